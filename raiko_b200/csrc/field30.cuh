@@ -1,0 +1,336 @@
+// BLS12-381 Fp / Fr arithmetic on 30-bit limbs (sm_100a first, host-compilable).
+//
+// Why 30-bit limbs: on B200 a carry-less IMAD.WIDE.U32 (32x32+64 -> 64) issues at
+// the full integer-multiply rate (measured 18.5 T/s, profiles/imad_ubench_r01.txt)
+// while the carry-chained form that mad.lo.cc / madc.hi.cc compile to
+// (IMAD.WIDE.U32.X with a predicate carry) runs at half of that.  With 30-bit
+// limbs a column of 13 partial products fits a 64-bit accumulator, so the whole
+// Montgomery product is 2*13^2+13 = 351 carry-less IMAD.WIDE/IMADs instead of
+// 300 carry-chained ones (= 600 issue slots); carries are resolved with a few
+// shifts on the otherwise idle ALU pipe.
+//
+// Representation: value = sum v[i] * 2^(30 i), every limb < 2^30 ("normalised").
+// Values are kept only loosely reduced: 0 <= value < 8*mod unless stated.  The
+// Montgomery radix is R = 2^(30 N) (2^390 for Fp, 2^270 for Fr) which leaves
+// 9 / 15 spare bits, so products never need a final conditional subtraction:
+//   mul(a, b) < a*b/R + mod   (a < 8 mod, b < 8 mod  =>  result < 1.11 mod).
+//
+// This file is the arithmetic the reference gets from the `bls12_381` crate
+// through rust-kzg (call sites lib/src/primitives/eip4844.rs:54-87); it is a
+// from-scratch formulation, not a translation of that crate's 64-bit limbs.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define RK_HD __host__ __device__ __forceinline__
+#define RK_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define RK_HD inline
+#define RK_HD_NOINLINE
+#endif
+
+#define RK_CONST_ARRAY(T, NAME, N, ...)                                  \
+    struct NAME {                                                        \
+        static constexpr int n = N;                                      \
+        RK_HD static constexpr T at(int i) {                             \
+            constexpr T t[N] = {__VA_ARGS__};                            \
+            return t[i];                                                 \
+        }                                                                \
+    };
+#include "kzg_constants.h"
+
+namespace rk {
+
+constexpr uint32_t LIMB_BITS = 30;
+constexpr uint32_t LIMB_MASK = (1u << LIMB_BITS) - 1u;
+
+// ---------------------------------------------------------------------------
+// Field configuration tags
+// ---------------------------------------------------------------------------
+struct FpTag {
+    static constexpr int N = FP_N;           // 13 limbs
+    static constexpr int W32 = 12;           // packed 32-bit words
+    static constexpr uint32_t PINV = FP_PINV;
+    static constexpr uint32_t MINV = FP_MINV;
+    using MOD = FP_MOD; using ONE = FP_ONE; using R2 = FP_R2;
+    using FROM_REF = FP_FROM_REF; using TO_REF = FP_TO_REF;
+    using EXP_INV = FP_EXP_INV;
+    RK_HD static constexpr uint32_t modx(int k, int i) {
+        return k == 1 ? FP_MOD::at(i) : k == 2 ? FP_MOD_X2::at(i) : k == 3 ? FP_MOD_X3::at(i)
+             : k == 4 ? FP_MOD_X4::at(i) : k == 5 ? FP_MOD_X5::at(i) : k == 6 ? FP_MOD_X6::at(i)
+             : k == 7 ? FP_MOD_X7::at(i) : FP_MOD_X8::at(i);
+    }
+};
+struct FrTag {
+    static constexpr int N = FR_N;           // 9 limbs
+    static constexpr int W32 = 8;
+    static constexpr uint32_t PINV = FR_PINV;
+    static constexpr uint32_t MINV = FR_MINV;
+    using MOD = FR_MOD; using ONE = FR_ONE; using R2 = FR_R2;
+    using FROM_REF = FR_FROM_REF; using TO_REF = FR_TO_REF;
+    using EXP_INV = FR_EXP_INV;
+    RK_HD static constexpr uint32_t modx(int k, int i) {
+        return k == 1 ? FR_MOD::at(i) : k == 2 ? FR_MOD_X2::at(i) : k == 3 ? FR_MOD_X3::at(i)
+             : k == 4 ? FR_MOD_X4::at(i) : k == 5 ? FR_MOD_X5::at(i) : k == 6 ? FR_MOD_X6::at(i)
+             : k == 7 ? FR_MOD_X7::at(i) : FR_MOD_X8::at(i);
+    }
+};
+
+template <class F>
+struct Fe {
+    uint32_t v[F::N];
+};
+
+// c += a * b  (32 x 32 + 64 -> 64, no carry out): one IMAD.WIDE.U32.
+RK_HD void mac(uint64_t& c, uint32_t a, uint32_t b) { c += (uint64_t)a * b; }
+
+// Hide a 32-bit value's provenance from the optimiser (emits no instruction).
+// Without this, LLVM sees `(uint64_t)(x & 0x3fffffff) * y`, rewrites the operand
+// as a 64-bit AND, can no longer select mul.wide.u32, and ptxas leaves a dead
+// "+ 0" IADD3 (the known-zero high cross term) behind every IMAD.WIDE.
+RK_HD uint32_t launder(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    asm("" : "+r"(x));
+#endif
+    return x;
+}
+
+using Fp = Fe<FpTag>;
+using Fr = Fe<FrTag>;
+
+// ---------------------------------------------------------------------------
+// Montgomery reduction of 2N-1 product columns (shared by mul and sqr)
+//   c[k] < 2^63.71 on entry (at most N products of two 30-bit limbs).
+// ---------------------------------------------------------------------------
+template <class F>
+RK_HD void mont_reduce_columns(Fe<F>& r, uint64_t (&c)[2 * F::N]) {
+    constexpr int N = F::N;
+    // A column k holds min(k+1, 2N-1-k) products now and receives as many m*mod
+    // products below.  More than 7+7 could overflow 64 bits, so split those
+    // columns first (carry-save: no ripple, every step independent).
+    constexpr int HOT_LO = 7, HOT_HI = 2 * N - 2 - 7;
+    if (HOT_LO <= HOT_HI) {
+        uint64_t carry_in = 0;
+#pragma unroll
+        for (int k = HOT_LO; k <= HOT_HI; k++) {
+            uint64_t hi = c[k] >> LIMB_BITS;
+            c[k] = (c[k] & LIMB_MASK) + carry_in;
+            carry_in = hi;
+        }
+        c[HOT_HI + 1] += carry_in;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint32_t m = launder(((uint32_t)c[i] * F::PINV) & LIMB_MASK);
+#pragma unroll
+        for (int j = 0; j < N; j++) mac(c[i + j], m, F::MOD::at(j));
+        c[i + 1] += c[i] >> LIMB_BITS;   // low 30 bits of c[i] are zero now
+    }
+    // result = columns N .. 2N-1, normalised
+#pragma unroll
+    for (int k = N; k < 2 * N - 1; k++) {
+        c[k + 1] += c[k] >> LIMB_BITS;
+        r.v[k - N] = launder((uint32_t)c[k] & LIMB_MASK);
+    }
+    r.v[N - 1] = launder((uint32_t)c[2 * N - 1]);
+}
+
+template <class F>
+RK_HD void fe_mul(Fe<F>& r, const Fe<F>& a, const Fe<F>& b) {
+    constexpr int N = F::N;
+    uint64_t c[2 * N];
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) c[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++) mac(c[i + j], a.v[i], b.v[j]);
+    mont_reduce_columns<F>(r, c);
+}
+
+template <class F>
+RK_HD void fe_sqr(Fe<F>& r, const Fe<F>& a) {
+    constexpr int N = F::N;
+    uint64_t c[2 * N];
+    uint32_t a2[N];
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) c[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) a2[i] = launder(a.v[i] << 1);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        mac(c[2 * i], a.v[i], a.v[i]);
+#pragma unroll
+        for (int j = i + 1; j < N; j++) mac(c[i + j], a2[i], a.v[j]);
+    }
+    mont_reduce_columns<F>(r, c);
+}
+
+// r = a + b, normalised.  No modular reduction: the caller tracks the bound.
+template <class F>
+RK_HD void fe_add(Fe<F>& r, const Fe<F>& a, const Fe<F>& b) {
+    uint32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+        uint32_t t = a.v[i] + b.v[i] + carry;
+        carry = t >> LIMB_BITS;
+        r.v[i] = launder(t & LIMB_MASK);
+    }
+}
+
+// r = a - b + K*mod  (K in 1..8, caller guarantees b <= K*mod so r >= 0)
+template <class F, int K>
+RK_HD void fe_sub(Fe<F>& r, const Fe<F>& a, const Fe<F>& b) {
+    int32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+        int32_t t = (int32_t)(a.v[i] + F::modx(K, i)) - (int32_t)b.v[i] + carry;
+        carry = t >> LIMB_BITS;                 // arithmetic shift: -1, 0 or 1
+        r.v[i] = launder((uint32_t)t & LIMB_MASK);
+    }
+}
+
+// r = K*mod - a
+template <class F, int K>
+RK_HD void fe_neg(Fe<F>& r, const Fe<F>& a) {
+    int32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+        int32_t t = (int32_t)F::modx(K, i) - (int32_t)a.v[i] + carry;
+        carry = t >> LIMB_BITS;
+        r.v[i] = launder((uint32_t)t & LIMB_MASK);
+    }
+}
+
+template <class F>
+RK_HD void fe_dbl(Fe<F>& r, const Fe<F>& a) { fe_add<F>(r, a, a); }
+
+template <class F>
+RK_HD void fe_set(Fe<F>& r, const Fe<F>& a) {
+#pragma unroll
+    for (int i = 0; i < F::N; i++) r.v[i] = a.v[i];
+}
+template <class F, class C>
+RK_HD void fe_const(Fe<F>& r) {
+#pragma unroll
+    for (int i = 0; i < F::N; i++) r.v[i] = C::at(i);
+}
+template <class F>
+RK_HD void fe_zero(Fe<F>& r) {
+#pragma unroll
+    for (int i = 0; i < F::N; i++) r.v[i] = 0;
+}
+
+// a == k*mod for some 0 <= k <= 8 ?  (a < 9*mod).  Cheap reject on limb 0.
+template <class F>
+RK_HD bool fe_is_zero_mod(const Fe<F>& a) {
+    uint32_t k = (a.v[0] * F::MINV) & LIMB_MASK;   // a = k*mod  =>  a0 = k*mod0 (mod 2^30)
+    if (k > 8) return false;
+    bool eq = true;
+    uint64_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+        uint64_t e = (uint64_t)k * F::MOD::at(i) + carry;     // < 9 * 2^30
+        carry = e >> LIMB_BITS;
+        eq = eq && (a.v[i] == ((uint32_t)e & LIMB_MASK));
+    }
+    return eq;
+}
+
+// a >= b as integers (both normalised)
+template <class F>
+RK_HD bool fe_geq_limbs(const Fe<F>& a, const uint32_t* b) {
+    for (int i = F::N - 1; i >= 0; i--) {
+        if (a.v[i] > b[i]) return true;
+        if (a.v[i] < b[i]) return false;
+    }
+    return true;
+}
+
+// Fully reduce a value < 2*mod into [0, mod).
+template <class F>
+RK_HD void fe_cond_sub_mod(Fe<F>& a) {
+    uint32_t t[F::N];
+    int32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+        int32_t d = (int32_t)a.v[i] - (int32_t)F::MOD::at(i) + carry;
+        carry = d >> LIMB_BITS;
+        t[i] = (uint32_t)d & LIMB_MASK;
+    }
+    if (carry == 0) {
+#pragma unroll
+        for (int i = 0; i < F::N; i++) a.v[i] = t[i];
+    }
+}
+
+// Montgomery -> canonical integer in [0, mod)
+template <class F>
+RK_HD void fe_from_mont(Fe<F>& r, const Fe<F>& a) {
+    Fe<F> one;
+    fe_zero<F>(one);
+    one.v[0] = 1;
+    fe_mul<F>(r, a, one);          // < a/R + mod < 2 mod
+    fe_cond_sub_mod<F>(r);
+}
+// canonical (or any value < 8 mod) -> Montgomery
+template <class F>
+RK_HD void fe_to_mont(Fe<F>& r, const Fe<F>& a) {
+    Fe<F> r2;
+    fe_const<F, typename F::R2>(r2);
+    fe_mul<F>(r, a, r2);
+}
+
+// 32-bit packed words <-> 30-bit limbs (value must be < 2^(32*W32))
+template <class F>
+RK_HD void fe_unpack(Fe<F>& r, const uint32_t* w) {
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+        const int bit = 30 * i, wi = bit >> 5, sh = bit & 31;
+        uint32_t lo = wi < F::W32 ? w[wi] : 0u;
+        uint32_t hi = (wi + 1) < F::W32 ? w[wi + 1] : 0u;
+        uint32_t x = sh == 0 ? lo : ((lo >> sh) | (sh > 2 ? (hi << (32 - sh)) : 0u));
+        r.v[i] = launder(x & LIMB_MASK);
+    }
+}
+template <class F>
+RK_HD void fe_pack(uint32_t* w, const Fe<F>& a) {
+#pragma unroll
+    for (int k = 0; k < F::W32; k++) {
+        const int bit = 32 * k, li = bit / 30, sh = bit % 30;   // word k starts inside limb li
+        uint32_t x = a.v[li] >> sh;
+        if (li + 1 < F::N) x |= a.v[li + 1] << (30 - sh);
+        w[k] = x;
+    }
+}
+
+// r = a^e, e given as little-endian 32-bit words from a constant table.
+// 4-bit fixed window: nbits squarings + nbits/4 multiplications.
+template <class F, class EXP, int NW>
+RK_HD_NOINLINE void fe_pow_const(Fe<F>& r, const Fe<F>& a) {
+    Fe<F> tab[16];
+    fe_const<F, typename F::ONE>(tab[0]);
+    fe_set<F>(tab[1], a);
+    for (int i = 2; i < 16; i++) fe_mul<F>(tab[i], tab[i - 1], a);
+    Fe<F> acc;
+    fe_const<F, typename F::ONE>(acc);
+    for (int w = NW - 1; w >= 0; w--) {
+        uint32_t word = EXP::at(w);
+        for (int nib = 7; nib >= 0; nib--) {
+            for (int s = 0; s < 4; s++) fe_sqr<F>(acc, acc);
+            uint32_t d = (word >> (4 * nib)) & 15u;
+            Fe<F> t;
+            fe_set<F>(t, tab[d]);
+            fe_mul<F>(acc, acc, t);
+        }
+    }
+    fe_set<F>(r, acc);
+}
+
+// Fermat inversion (0 -> 0).  Input < 8 mod, output < 1.11 mod.
+template <class F>
+RK_HD void fe_inv(Fe<F>& r, const Fe<F>& a) {
+    fe_pow_const<F, typename F::EXP_INV, F::W32>(r, a);
+}
+
+}  // namespace rk

@@ -1,0 +1,246 @@
+// BLS12-381 G1 in extended Jacobian ("XYZZ") coordinates on top of field30.cuh.
+//
+// x = X/ZZ, y = Y/ZZZ with ZZ^3 = ZZZ^2.  Infinity is ZZ == 0 (all limbs zero,
+// set explicitly -- a product of non-zero residues is never 0 mod p).
+// Formulas: madd-2008-s / add-2008-s / dbl-2008-s-1 (a = 0).  Every exceptional
+// case (infinity operands, P + P, P + (-P)) is handled, so the MSM built on
+// these is exact for arbitrary scalars, which the bit-exact parity bar needs.
+//
+// Bounds (p = modulus): accumulator X, Y < 6p; ZZ, ZZZ < 1.1p; affine operand
+// coordinates < 2p.  See field30.cuh for why no reduction is ever needed.
+//
+// Replaces the G1Projective arithmetic rust-kzg's g1_lincomb runs for
+// blob_to_kzg_commitment_rust / compute_kzg_proof_rust
+// (reference call sites lib/src/primitives/eip4844.rs:75,85).
+#pragma once
+#include "field30.cuh"
+
+namespace rk {
+
+struct G1Affine {
+    Fp x, y;
+};
+struct G1Xyzz {
+    Fp x, y, zz, zzz;
+};
+
+RK_HD void g1_set_inf(G1Xyzz& a) {
+    fe_zero(a.x); fe_zero(a.y); fe_zero(a.zz); fe_zero(a.zzz);
+}
+RK_HD bool g1_is_inf(const G1Xyzz& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < FP_N; i++) o |= a.zz.v[i];
+    return o == 0;
+}
+RK_HD void g1_from_affine(G1Xyzz& r, const G1Affine& p) {
+    fe_set(r.x, p.x); fe_set(r.y, p.y);
+    fe_const<FpTag, FP_ONE>(r.zz); fe_const<FpTag, FP_ONE>(r.zzz);
+}
+
+// r = 2 * (x, y, zz, zzz); works for affine input with zz = zzz = 1 too.
+RK_HD void g1_dbl(G1Xyzz& r, const G1Xyzz& a) {
+    if (g1_is_inf(a)) { g1_set_inf(r); return; }
+    Fp U, V, Wv, S, M, t, X3;
+    fe_dbl(U, a.y);                 // < 12p
+    fe_sqr(V, U);                   // < 1.3p
+    fe_mul(Wv, U, V);
+    fe_mul(S, a.x, V);
+    fe_sqr(t, a.x);
+    fe_add(M, t, t); fe_add(M, M, t);      // 3 X^2 < 3.4p
+    fe_sqr(X3, M);
+    fe_add(t, S, S);                        // 2S < 2.1p
+    fe_sub<FpTag, 4>(X3, X3, t);            // < 5.1p
+    fe_sub<FpTag, 6>(t, S, X3);             // < 7.1p
+    fe_mul(t, M, t);
+    fe_mul(U, Wv, a.y);                     // W*Y1 < 1.1p
+    fe_mul(r.zz, V, a.zz);
+    fe_mul(r.zzz, Wv, a.zzz);
+    fe_sub<FpTag, 2>(r.y, t, U);
+    fe_set(r.x, X3);
+}
+
+// acc += (x2, y2) affine (never infinity).
+RK_HD void g1_madd(G1Xyzz& acc, const Fp& x2, const Fp& y2) {
+    if (g1_is_inf(acc)) {
+        fe_set(acc.x, x2); fe_set(acc.y, y2);
+        fe_const<FpTag, FP_ONE>(acc.zz); fe_const<FpTag, FP_ONE>(acc.zzz);
+        return;
+    }
+    Fp P, Rr, PP, PPP, Q, t;
+    fe_mul(P, x2, acc.zz);
+    fe_mul(Rr, y2, acc.zzz);
+    fe_sub<FpTag, 6>(P, P, acc.x);          // < 7.1p
+    fe_sub<FpTag, 6>(Rr, Rr, acc.y);
+    if (fe_is_zero_mod(P)) {
+        if (fe_is_zero_mod(Rr)) {
+            G1Xyzz d;
+            fe_set(d.x, x2); fe_set(d.y, y2);
+            fe_const<FpTag, FP_ONE>(d.zz); fe_const<FpTag, FP_ONE>(d.zzz);
+            g1_dbl(acc, d);
+        } else {
+            g1_set_inf(acc);
+        }
+        return;
+    }
+    fe_sqr(PP, P);
+    fe_mul(PPP, P, PP);
+    fe_mul(Q, acc.x, PP);
+    fe_sqr(acc.x, Rr);                      // X3 = R^2 - PPP - 2Q
+    fe_add(t, Q, Q);
+    fe_add(t, t, PPP);                      // < 3.1p
+    fe_sub<FpTag, 4>(acc.x, acc.x, t);      // < 5.1p
+    fe_sub<FpTag, 6>(t, Q, acc.x);          // < 7.1p
+    fe_mul(t, Rr, t);
+    fe_mul(Q, acc.y, PPP);
+    fe_sub<FpTag, 2>(acc.y, t, Q);          // < 3.1p
+    fe_mul(acc.zz, acc.zz, PP);
+    fe_mul(acc.zzz, acc.zzz, PPP);
+}
+
+// a += b (both XYZZ)
+RK_HD void g1_add(G1Xyzz& a, const G1Xyzz& b) {
+    if (g1_is_inf(b)) return;
+    if (g1_is_inf(a)) { a = b; return; }
+    Fp U1, S1, P, Rr, PP, PPP, Q, t;
+    fe_mul(U1, a.x, b.zz);
+    fe_mul(P, b.x, a.zz);
+    fe_mul(S1, a.y, b.zzz);
+    fe_mul(Rr, b.y, a.zzz);
+    fe_sub<FpTag, 2>(P, P, U1);             // < 3.1p
+    fe_sub<FpTag, 2>(Rr, Rr, S1);
+    if (fe_is_zero_mod(P)) {
+        if (fe_is_zero_mod(Rr)) {
+            G1Xyzz d = a;
+            g1_dbl(a, d);
+        } else {
+            g1_set_inf(a);
+        }
+        return;
+    }
+    fe_sqr(PP, P);
+    fe_mul(PPP, P, PP);
+    fe_mul(Q, U1, PP);
+    fe_sqr(a.x, Rr);
+    fe_add(t, Q, Q);
+    fe_add(t, t, PPP);
+    fe_sub<FpTag, 4>(a.x, a.x, t);
+    fe_sub<FpTag, 6>(t, Q, a.x);
+    fe_mul(t, Rr, t);
+    fe_mul(Q, S1, PPP);
+    fe_sub<FpTag, 2>(a.y, t, Q);
+    fe_mul(a.zz, a.zz, b.zz);
+    fe_mul(a.zz, a.zz, PP);
+    fe_mul(a.zzz, a.zzz, b.zzz);
+    fe_mul(a.zzz, a.zzz, PPP);
+}
+
+// XYZZ -> affine Montgomery coordinates (< 1.1p); returns false for infinity.
+// `zzz_inv` must be 1/ZZZ (Montgomery); callers batch that inversion.
+RK_HD void g1_to_affine_with_inv(G1Affine& r, const G1Xyzz& a, const Fp& zzz_inv) {
+    Fp t;
+    fe_mul(t, a.zz, zzz_inv);      // ZZ/ZZZ
+    fe_sqr(t, t);                  // = 1/ZZ   (ZZ^3 = ZZZ^2)
+    fe_mul(r.x, a.x, t);
+    fe_mul(r.y, a.y, zzz_inv);
+}
+
+// ---------------------------------------------------------------------------
+// Serialisation (reference ZG1::to_bytes via
+// kzg_proof_to_bytes, lib/src/primitives/eip4844.rs:97-99)
+// ---------------------------------------------------------------------------
+// canonical integer limbs -> 48 big-endian bytes
+RK_HD void fp_to_be48(uint8_t* out, const Fp& canon) {
+    uint32_t w[12];
+    fe_pack<FpTag>(w, canon);
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        uint32_t x = w[11 - k];
+        out[4 * k + 0] = (uint8_t)(x >> 24);
+        out[4 * k + 1] = (uint8_t)(x >> 16);
+        out[4 * k + 2] = (uint8_t)(x >> 8);
+        out[4 * k + 3] = (uint8_t)x;
+    }
+}
+
+// x, y Montgomery (< 8p).  Writes the 48-byte zcash compressed form.
+RK_HD void g1_compress_affine(uint8_t* out, const G1Affine& p) {
+    Fp x, y;
+    fe_from_mont(x, p.x);
+    fe_from_mont(y, p.y);
+    fp_to_be48(out, x);
+    // y > (p-1)/2 ?
+    bool gt = false, decided = false;
+    for (int i = FP_N - 1; i >= 0; i--) {
+        uint32_t h = FP_HALF::at(i);
+        if (!decided && y.v[i] != h) { gt = y.v[i] > h; decided = true; }
+    }
+    out[0] |= gt ? 0xA0 : 0x80;
+}
+RK_HD void g1_compress_inf(uint8_t* out) {
+    out[0] = 0xC0;
+    for (int i = 1; i < 48; i++) out[i] = 0;
+}
+
+// Full conversion of one XYZZ point (one Fermat inversion; used per output).
+RK_HD void g1_compress(uint8_t* out, const G1Xyzz& a) {
+    if (g1_is_inf(a)) { g1_compress_inf(out); return; }
+    Fp inv;
+    fe_inv(inv, a.zzz);
+    G1Affine aff;
+    g1_to_affine_with_inv(aff, a, inv);
+    g1_compress_affine(out, aff);
+}
+
+// 48 compressed bytes -> affine Montgomery.  Returns 0 ok, 1 infinity, <0 error.
+// No subgroup check (the trusted setup is validated against its known digest).
+RK_HD int g1_decompress(G1Affine& r, const uint8_t* in) {
+    if (!(in[0] & 0x80)) return -1;
+    if (in[0] & 0x40) {
+        uint32_t o = in[0] & 0x3F;
+        for (int i = 1; i < 48; i++) o |= in[i];
+        return o ? -2 : 1;
+    }
+    uint32_t w[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const uint8_t* b = in + 4 * (11 - k);
+        uint32_t first = (k == 11) ? (uint32_t)(b[0] & 0x1F) : (uint32_t)b[0];
+        w[k] = (first << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | (uint32_t)b[3];
+    }
+    Fp xc;
+    fe_unpack<FpTag>(xc, w);
+    // x < p ?
+    {
+        bool lt = false, decided = false;
+        for (int i = FP_N - 1; i >= 0; i--) {
+            uint32_t m = FP_MOD::at(i);
+            if (!decided && xc.v[i] != m) { lt = xc.v[i] < m; decided = true; }
+        }
+        if (!lt) return -3;
+    }
+    Fp x, rhs, y, t, b4;
+    fe_to_mont(x, xc);
+    fe_sqr(rhs, x);
+    fe_mul(rhs, rhs, x);
+    fe_const<FpTag, FP_B_COEFF>(b4);
+    fe_add(rhs, rhs, b4);                          // x^3 + 4  (< 2.1p)
+    fe_pow_const<FpTag, FP_EXP_SQRT, 12>(y, rhs);
+    fe_sqr(t, y);
+    fe_sub<FpTag, 4>(t, t, rhs);
+    if (!fe_is_zero_mod(t)) return -4;             // not on the curve
+    Fp yc;
+    fe_from_mont(yc, y);
+    bool gt = false, decided = false;
+    for (int i = FP_N - 1; i >= 0; i--) {
+        uint32_t h = FP_HALF::at(i);
+        if (!decided && yc.v[i] != h) { gt = yc.v[i] > h; decided = true; }
+    }
+    bool want = (in[0] & 0x20) != 0;
+    if (gt != want) fe_neg<FpTag, 2>(y, y);
+    fe_set(r.x, x);
+    fe_set(r.y, y);
+    return 0;
+}
+
+}  // namespace rk
