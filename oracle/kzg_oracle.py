@@ -326,11 +326,15 @@ def load_settings(data: bytes) -> Settings:
         roots_off, g1_off, g2_off = 262_264 + 8, 393_344 + 8, 983_176 + 8
         assert int.from_bytes(data[393_344:393_352], "little") == n
         assert data[-1] == 0  # precomputation = None
-    elif data[:8] == b"RKZGTS01":
+    elif data[:8] == b"RKZGTS02":
+        # compact image: compressed G1, uncompressed affine G2 (x.c0|x.c1|y.c0|y.c1, 48 B BE each)
         ng1, ng2 = struct.unpack("<II", data[8:16])
         g1 = [g1_decompress(data[16 + 48 * i:16 + 48 * i + 48]) for i in range(ng1)]
         off = 16 + 48 * ng1
-        g2 = [g2_decompress(data[off + 96 * i:off + 96 * i + 96]) for i in range(ng2)]
+        g2 = []
+        for i in range(ng2):
+            v = [int.from_bytes(data[off + 192 * i + 48 * k:off + 192 * i + 48 * k + 48], "big") for k in range(4)]
+            g2.append(((v[0], v[1]), (v[2], v[3])))
         return Settings(g1, g2, roots_of_unity_brp(ng1))
     else:
         raise ValueError("unknown settings image (len %d)" % len(data))

@@ -1,0 +1,841 @@
+// Host side of libraiko_kzg.so: settings decoding, window-table construction, the
+// chunked multi-stream batch scheduler, multi-GPU sharding and the C ABI declared in
+// include/raiko_kzg.h.  No CPU arithmetic lives here: every field / curve operation
+// runs in the kernels of kzg_kernels.cuh; without a CUDA device the entry points
+// fail with RK_ERR_CUDA (no fallback, by design).
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/raiko_kzg.h"
+#include "kzg_kernels.cuh"
+
+using namespace rk;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+rk_status fail(rk_status st, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return st;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(RK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+constexpr size_t RAW_LEN = 739624, BINCODE_LEN = 1001905;
+constexpr size_t RAW_ROOTS = 8, RAW_G1 = 131080, RAW_G2 = 720904;
+constexpr size_t BC_EXPANDED = 40, BC_REVERSE = 131152, BC_ROOTS = 262264, BC_G1 = 393344, BC_G2 = 983176;
+constexpr int N_G2 = 65;
+
+TableGeom make_geom(int c) {
+    TableGeom g;
+    g.c = c;
+    g.W = (255 + c - 1) / c;
+    g.half = 1u << (c - 1);
+    // top digit = (r - 1) >> c(W-1), plus the carry of the signed digit below it
+    const int sh = c * (g.W - 1);
+    // r as 32-bit words (little endian)
+    uint32_t top = 0;
+    for (int bit = 0; bit < 32 && sh + bit < 256; bit++) {
+        int b = sh + bit;
+        uint32_t w = FR_MOD_W32::at(b >> 5);
+        top |= ((w >> (b & 31)) & 1u) << bit;
+    }
+    g.top_entries = top + 1;
+    g.per_point = (uint32_t)(g.W - 1) * g.half + g.top_entries;
+    return g;
+}
+
+struct KernelTimer {   // optional CUDA-event pair around a launch
+    cudaEvent_t a = nullptr, b = nullptr;
+    int kind = 0;
+};
+
+struct ChunkSlot {
+    uint8_t* d_blobs = nullptr;     // chunk * 131072 (host-input path only)
+    uint8_t* d_q = nullptr;         // chunk * 131072 quotient scalars
+    G1Xyzz* d_partials = nullptr;   // chunk * max_splits... sized for max(chunk, small-batch splits)
+    uint8_t* d_out = nullptr;       // per blob: C48 | vh32 | x32 | y32 | proof48 | hash32 | status1(+pad)
+    uint8_t* d_zin = nullptr;       // chunk * 32 (compute_kzg_proof inputs)
+    uint32_t* d_bad = nullptr;      // chunk
+    uint8_t* h_out = nullptr;       // pinned mirror of d_out
+    uint8_t* h_in = nullptr;        // pinned staging for pageable host input (lazy)
+    cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_done = nullptr, ev_out = nullptr;
+    bool busy = false;
+    size_t first = 0, count = 0;    // blobs of the batch this slot currently holds
+};
+
+constexpr int OUT_STRIDE = 224;     // 48+32+32+32+48+32 = 224
+constexpr int OFF_C = 0, OFF_VH = 48, OFF_X = 80, OFF_Y = 112, OFF_PROOF = 144, OFF_HASH = 192;
+
+struct DeviceCtx {
+    int dev = 0;
+    TableGeom geom{};
+    TableEntry* table = nullptr;
+    uint64_t table_bytes = 0;
+    Fr* roots = nullptr;
+    G1Affine* g1_aff = nullptr;            // 4096 setup points, affine Montgomery
+    cudaStream_t s_main = nullptr, s_sha = nullptr, s_in = nullptr, s_out = nullptr;
+    int chunk = 0;
+    int max_partials = 0;
+    ChunkSlot slot[2];
+    uint8_t* d_status = nullptr;           // chunk (status bytes), part of d_out really
+    std::mutex mu;
+    int sm_count = 148;
+    // stats
+    bool stats_on = false;
+    std::vector<KernelTimer> timers;
+    rk_kzg_stats stats{};
+};
+
+}  // namespace
+
+struct rk_kzg_ctx {
+    std::vector<DeviceCtx*> devs;
+    TableGeom geom{};
+    std::vector<uint8_t> g2_be;            // 65 * 192 bytes (x.c0|x.c1|y.c0|y.c1 big-endian canonical)
+};
+
+namespace {
+
+enum { T_MSM = 1, T_FR = 2, T_SHA = 3, T_FIN = 4 };
+
+void timer_begin(DeviceCtx* d, cudaStream_t s, int kind) {
+    d->stats.total_launches++;
+    if (kind == T_MSM) d->stats.msm_launches++;
+    if (!d->stats_on) return;
+    KernelTimer t;
+    t.kind = kind;
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+    cudaEventRecord(t.a, s);
+    d->timers.push_back(t);
+}
+void timer_end(DeviceCtx* d, cudaStream_t s) {
+    if (!d->stats_on) return;
+    cudaEventRecord(d->timers.back().b, s);
+}
+void timers_collect(DeviceCtx* d) {   // call after the streams are synchronised
+    for (auto& t : d->timers) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            if (t.kind == T_MSM) d->stats.msm_ms += ms;
+            if (t.kind == T_FR) d->stats.fr_ms += ms;
+            if (t.kind == T_SHA) d->stats.sha_ms += ms;
+            if (t.kind == T_FIN) d->stats.finalize_ms += ms;
+        }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    d->timers.clear();
+}
+
+void free_device(DeviceCtx* d) {
+    if (!d) return;
+    cudaSetDevice(d->dev);
+    for (auto& s : d->slot) {
+        cudaFree(s.d_blobs); cudaFree(s.d_q); cudaFree(s.d_partials); cudaFree(s.d_out);
+        cudaFree(s.d_zin); cudaFree(s.d_bad);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.ev_in) cudaEventDestroy(s.ev_in);
+        if (s.ev_sha) cudaEventDestroy(s.ev_sha);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.ev_out) cudaEventDestroy(s.ev_out);
+    }
+    cudaFree(d->table); cudaFree(d->roots); cudaFree(d->g1_aff);
+    if (d->s_main) cudaStreamDestroy(d->s_main);
+    if (d->s_sha) cudaStreamDestroy(d->s_sha);
+    if (d->s_in) cudaStreamDestroy(d->s_in);
+    if (d->s_out) cudaStreamDestroy(d->s_out);
+    delete d;
+}
+
+// Decode the settings image into affine Montgomery G1 points on the device and the
+// big-endian G2 coordinates on the host.
+rk_status load_setup(DeviceCtx* d, const uint8_t* data, size_t len, std::vector<uint8_t>* g2_be) {
+    CUDA_TRY(cudaMalloc(&d->g1_aff, sizeof(G1Affine) * NPTS));
+    int* d_err = nullptr;
+    CUDA_TRY(cudaMalloc(&d_err, sizeof(int)));
+    CUDA_TRY(cudaMemset(d_err, 0, sizeof(int)));
+    uint8_t* d_in = nullptr;
+    size_t g1_off = 0, g2_off = 0;
+    bool ref_format = false;
+    if (len == RAW_LEN) {
+        if (!(data[6] == 0x10 && data[7] == 0x00 && data[0] == 0)) return fail(RK_ERR_BAD_SETTINGS, "raw settings: max_width != 4096");
+        g1_off = RAW_G1; g2_off = RAW_G2; ref_format = true;
+    } else if (len == BINCODE_LEN) {
+        uint64_t w = 0, n1 = 0, n2 = 0;
+        memcpy(&w, data, 8); memcpy(&n1, data + BC_G1, 8); memcpy(&n2, data + BC_G2, 8);
+        if (w != 4096 || n1 != 4096 || n2 != N_G2 || data[len - 1] != 0)
+            return fail(RK_ERR_BAD_SETTINGS, "bincode settings: unexpected header fields");
+        g1_off = BC_G1 + 8; g2_off = BC_G2 + 8; ref_format = true;
+    } else if (len >= 16 && memcmp(data, "RKZGTS02", 8) == 0) {
+        uint32_t n1, n2;
+        memcpy(&n1, data + 8, 4); memcpy(&n2, data + 12, 4);
+        if (n1 != NPTS || n2 != N_G2 || len != 16 + 48ull * n1 + 192ull * n2)
+            return fail(RK_ERR_BAD_SETTINGS, "compact settings: bad counts / length");
+        g1_off = 16; g2_off = 16 + 48ull * n1;
+    } else {
+        return fail(RK_ERR_BAD_SETTINGS, "unrecognised settings image (%zu bytes)", len);
+    }
+    const size_t g1_bytes = ref_format ? 144ull * NPTS : 48ull * NPTS;
+    CUDA_TRY(cudaMalloc(&d_in, g1_bytes));
+    CUDA_TRY(cudaMemcpy(d_in, data + g1_off, g1_bytes, cudaMemcpyHostToDevice));
+    if (ref_format) k_setup_from_ref<<<NPTS / 64, 64>>>(d_in, NPTS, d->g1_aff, d_err);
+    else k_setup_decompress<<<NPTS / 64, 64>>>(d_in, NPTS, d->g1_aff, d_err);
+    CUDA_TRY(cudaGetLastError());
+    int err = 0;
+    CUDA_TRY(cudaMemcpy(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_in);
+    cudaFree(d_err);
+    if (err) return fail(RK_ERR_BAD_SETTINGS, "setup G1 point %d is not a valid affine curve point", err - 1);
+    if (g2_be) {
+        g2_be->resize(192 * N_G2);
+        if (!ref_format) {
+            memcpy(g2_be->data(), data + g2_off, 192 * N_G2);
+        } else {
+            // 65 x (X.c0 X.c1 Y.c0 Y.c1 Z.c0 Z.c1) Montgomery limbs -> big-endian canonical x, y
+            uint8_t *d_g2 = nullptr, *d_o = nullptr;
+            CUDA_TRY(cudaMalloc(&d_g2, 288 * N_G2));
+            CUDA_TRY(cudaMalloc(&d_o, 288 * N_G2));
+            CUDA_TRY(cudaMemcpy(d_g2, data + g2_off, 288 * N_G2, cudaMemcpyHostToDevice));
+            k_fp_ref_to_be<<<(6 * N_G2 + 63) / 64, 64>>>(d_g2, 6 * N_G2, d_o);
+            std::vector<uint8_t> tmp(288 * N_G2);
+            CUDA_TRY(cudaMemcpy(tmp.data(), d_o, tmp.size(), cudaMemcpyDeviceToHost));
+            cudaFree(d_g2); cudaFree(d_o);
+            for (int i = 0; i < N_G2; i++) {
+                const uint8_t* p = tmp.data() + 288 * i;
+                // Z must be (1, 0)
+                bool z_ok = p[4 * 48 + 47] == 1;
+                for (int k = 0; k < 47; k++) z_ok = z_ok && p[4 * 48 + k] == 0;
+                for (int k = 0; k < 48; k++) z_ok = z_ok && p[5 * 48 + k] == 0;
+                if (!z_ok) return fail(RK_ERR_BAD_SETTINGS, "setup G2 point %d is not affine", i);
+                memcpy(g2_be->data() + 192 * i, p, 192);
+            }
+        }
+    }
+    return RK_OK;
+}
+
+rk_status build_table(DeviceCtx* d) {
+    const TableGeom g = d->geom;
+    const size_t entries = (size_t)NPTS * g.per_point;
+    d->table_bytes = entries * sizeof(TableEntry);
+    CUDA_TRY(cudaMalloc(&d->table, d->table_bytes));
+    const int chains = NPTS * g.W;
+    G1Xyzz *bases = nullptr, *state = nullptr, *tmp = nullptr;
+    G1Affine* bases_aff = nullptr;
+    CUDA_TRY(cudaMalloc(&bases, sizeof(G1Xyzz) * chains));
+    CUDA_TRY(cudaMalloc(&bases_aff, sizeof(G1Affine) * chains));
+    CUDA_TRY(cudaMalloc(&state, sizeof(G1Xyzz) * chains));
+    k_table_bases<<<NPTS / 64, 64>>>(d->g1_aff, g, bases);
+    k_table_bases_affine<<<(chains / 16 + 63) / 64, 64>>>(bases, chains, bases_aff);
+    CUDA_TRY(cudaGetLastError());
+    const uint32_t emax = std::max(g.half, g.top_entries);
+    int D = 256;
+    while ((uint32_t)D > emax && D > TABLE_NORM_G) D >>= 1;
+    CUDA_TRY(cudaMalloc(&tmp, sizeof(G1Xyzz) * (size_t)chains * D));
+    for (uint32_t d0 = 1; d0 <= emax; d0 += D) {
+        k_table_chain<<<(chains + 127) / 128, 128>>>(bases_aff, g, d0, D, state, tmp);
+        const long long groups = (long long)chains * (D / TABLE_NORM_G);
+        k_table_normalize<<<(unsigned)((groups + 127) / 128), 128>>>(g, d0, D, tmp, d->table);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(bases); cudaFree(bases_aff); cudaFree(state); cudaFree(tmp);
+    return RK_OK;
+}
+
+rk_status alloc_slots(DeviceCtx* d) {
+    // chunk: blobs per pipeline stage.  2 slots x (blobs + quotients) x 128 KiB.
+    d->chunk = 1024;
+    if (const char* e = getenv("RAIKO_KZG_CHUNK")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= 16384) d->chunk = v;
+    }
+    d->max_partials = std::max(d->chunk, 128 * 32);
+    for (auto& s : d->slot) {
+        CUDA_TRY(cudaMalloc(&s.d_q, (size_t)d->chunk * BLOB_BYTES));
+        CUDA_TRY(cudaMalloc(&s.d_partials, sizeof(G1Xyzz) * (size_t)d->max_partials));
+        CUDA_TRY(cudaMalloc(&s.d_out, (size_t)d->chunk * OUT_STRIDE + d->chunk));
+        CUDA_TRY(cudaMalloc(&s.d_zin, (size_t)d->chunk * 32));
+        CUDA_TRY(cudaMalloc(&s.d_bad, sizeof(uint32_t) * d->chunk));
+        CUDA_TRY(cudaMallocHost(&s.h_out, (size_t)d->chunk * OUT_STRIDE + d->chunk));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_sha, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    }
+    return RK_OK;
+}
+
+rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int window_bits,
+                      std::vector<uint8_t>* g2_be) {
+    CUDA_TRY(cudaSetDevice(d->dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, d->dev));
+    d->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10)
+        return fail(RK_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", d->dev, prop.major, prop.minor);
+    int c = window_bits;
+    if (c == 0) {
+        if (const char* e = getenv("RAIKO_KZG_WINDOW_BITS")) c = atoi(e);
+    }
+    if (c == 0) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        for (c = 15; c > 8; c--) {
+            TableGeom g = make_geom(c);
+            double need = (double)NPTS * g.per_point * sizeof(TableEntry) + 8e9;   // table + build scratch + chunk buffers
+            if (need < 0.80 * (double)free_b) break;
+        }
+    }
+    if (c < 4 || c > 15) return fail(RK_ERR_ARG, "window_bits %d outside 4..15", c);
+    d->geom = make_geom(c);
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_main, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_sha, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+    CUDA_TRY(cudaFuncSetAttribute(k_fr_eval_quot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM_BYTES));
+    rk_status st = load_setup(d, settings, len, g2_be);
+    if (st != RK_OK) return st;
+    CUDA_TRY(cudaMalloc(&d->roots, sizeof(Fr) * NPTS));
+    k_roots_brp<<<NPTS / 128, 128>>>(d->roots);
+    CUDA_TRY(cudaGetLastError());
+    st = build_table(d);
+    if (st != RK_OK) return st;
+    return alloc_slots(d);
+}
+
+// ----------------------------------------------------------------------------------------
+// Batch pipeline on one device
+// ----------------------------------------------------------------------------------------
+enum BatchMode { MODE_COMMIT = 0, MODE_COMMIT_PROVE = 1, MODE_PROOF_AT_Z = 2, MODE_EVAL_ONLY = 3, MODE_POINT_ONLY = 4 };
+
+struct BatchArgs {
+    BatchMode mode;
+    const uint8_t* blobs;        // shard base (host or device)
+    bool blobs_on_device;
+    const uint8_t* zs;           // MODE_PROOF_AT_Z: host, n*32
+    const uint8_t* vhs;          // MODE_EVAL_ONLY / MODE_POINT_ONLY: host, n*32
+    size_t n;
+    uint8_t *out_c, *out_vh, *out_x, *out_y, *out_proof, *status;   // host or device, may be null
+    bool outs_on_device;
+};
+
+int pick_splits_log2(const DeviceCtx* d, size_t nblobs) {
+    // enough warps to fill the machine (8 resident warps per SM), at most 32 per blob
+    const size_t target = (size_t)d->sm_count * 8;
+    int lg = 0;
+    while (lg < 5 && (nblobs << lg) < target) lg++;
+    return lg;
+}
+
+void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint32_t* bad, int* splits_out) {
+    MsmParams p;
+    p.table = d->table; p.g = d->geom; p.scalars = scalars; p.nblobs = n;
+    p.splits_log2 = pick_splits_log2(d, (size_t)n);
+    p.partials = s.d_partials; p.bad = bad;
+    const long long warps = (long long)n << p.splits_log2;
+    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    timer_begin(d, d->s_main, T_MSM);
+    k_msm<<<blocks, 256, 0, d->s_main>>>(p);
+    timer_end(d, d->s_main);
+    d->stats.msm_point_adds += (uint64_t)n * NPTS * d->geom.W;
+    *splits_out = 1 << p.splits_log2;
+}
+
+rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
+    std::lock_guard<std::mutex> lock(d->mu);
+    CUDA_TRY(cudaSetDevice(d->dev));
+    const size_t chunk = (size_t)d->chunk;
+    const size_t nchunks = (a.n + chunk - 1) / chunk;
+    auto drain = [&](ChunkSlot& s) -> rk_status {
+        if (!s.busy) return RK_OK;
+        CUDA_TRY(cudaEventSynchronize(s.ev_out));
+        s.busy = false;
+        if (a.outs_on_device) return RK_OK;
+        const uint8_t* stat = s.h_out + (size_t)d->chunk * OUT_STRIDE;
+        for (size_t i = 0; i < s.count; i++) {
+            const uint8_t* o = s.h_out + i * OUT_STRIDE;
+            const size_t gi = s.first + i;
+            if (a.out_c) memcpy(a.out_c + 48 * gi, o + OFF_C, 48);
+            if (a.out_vh) memcpy(a.out_vh + 32 * gi, o + OFF_VH, 32);
+            if (a.out_x) memcpy(a.out_x + 32 * gi, o + OFF_X, 32);
+            if (a.out_y) memcpy(a.out_y + 32 * gi, o + OFF_Y, 32);
+            if (a.out_proof) memcpy(a.out_proof + 48 * gi, o + OFF_PROOF, 48);
+            if (a.status) a.status[gi] = stat[i];
+        }
+        return RK_OK;
+    };
+
+    for (size_t ci = 0; ci < nchunks; ci++) {
+        ChunkSlot& s = d->slot[ci & 1];
+        rk_status st = drain(s);
+        if (st != RK_OK) return st;
+        const size_t first = ci * chunk;
+        const int cnt = (int)std::min(chunk, a.n - first);
+        s.first = first; s.count = (size_t)cnt; s.busy = true;
+
+        // ---- input ---------------------------------------------------------------------
+        const uint8_t* d_blobs;
+        if (a.blobs_on_device) {
+            d_blobs = a.blobs + first * BLOB_BYTES;
+        } else {
+            if (!s.d_blobs) CUDA_TRY(cudaMalloc(&s.d_blobs, chunk * BLOB_BYTES));
+            CUDA_TRY(cudaMemcpyAsync(s.d_blobs, a.blobs + first * BLOB_BYTES, (size_t)cnt * BLOB_BYTES,
+                                     cudaMemcpyHostToDevice, d->s_in));
+            d->stats.h2d_bytes += (uint64_t)cnt * BLOB_BYTES;
+            d_blobs = s.d_blobs;
+        }
+        if (a.mode == MODE_PROOF_AT_Z) {
+            CUDA_TRY(cudaMemcpyAsync(s.d_zin, a.zs + 32 * first, 32 * (size_t)cnt, cudaMemcpyHostToDevice, d->s_in));
+            d->stats.h2d_bytes += 32ull * cnt;
+        }
+        uint8_t* o = s.d_out;
+        uint8_t* o_stat = s.d_out + chunk * OUT_STRIDE;
+        if (a.mode == MODE_EVAL_ONLY || a.mode == MODE_POINT_ONLY) {
+            // caller-supplied versioned hashes go where the commit stage would have put them
+            CUDA_TRY(cudaMemcpy2DAsync(o + OFF_VH, OUT_STRIDE, a.vhs + 32 * first, 32, 32, (size_t)cnt,
+                                       cudaMemcpyHostToDevice, d->s_in));
+        }
+        CUDA_TRY(cudaEventRecord(s.ev_in, d->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(d->s_main, s.ev_in, 0));
+        CUDA_TRY(cudaMemsetAsync(s.d_bad, 0, sizeof(uint32_t) * cnt, d->s_main));
+        CUDA_TRY(cudaMemsetAsync(o_stat, 0, (size_t)cnt, d->s_main));
+
+        const bool need_hash = a.mode == MODE_COMMIT_PROVE || a.mode == MODE_EVAL_ONLY || a.mode == MODE_POINT_ONLY;
+        if (need_hash) {
+            CUDA_TRY(cudaStreamWaitEvent(d->s_sha, s.ev_in, 0));
+            timer_begin(d, d->s_sha, T_SHA);
+            k_sha_blob<<<(cnt + 31) / 32, 32, 0, d->s_sha>>>(d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
+            timer_end(d, d->s_sha);
+            CUDA_TRY(cudaEventRecord(s.ev_sha, d->s_sha));
+        }
+        int splits = 1;
+        // ---- commitment ------------------------------------------------------------------
+        if (a.mode == MODE_COMMIT || a.mode == MODE_COMMIT_PROVE) {
+            launch_msm(d, d_blobs, cnt, s, s.d_bad, &splits);
+            timer_begin(d, d->s_main, T_FIN);
+            k_finalize<<<(cnt + 31) / 32, 32, 0, d->s_main>>>(s.d_partials, splits, cnt, s.d_bad, o + OFF_C, o + OFF_VH,
+                                                              o_stat, OUT_STRIDE);
+            timer_end(d, d->s_main);
+        }
+        // ---- evaluation / quotient -------------------------------------------------------
+        if (a.mode != MODE_COMMIT) {
+            if (need_hash) CUDA_TRY(cudaStreamWaitEvent(d->s_main, s.ev_sha, 0));
+            FrParams fp;
+            fp.blobs = d_blobs; fp.roots_brp = d->roots;
+            fp.blob_hash = o + OFF_HASH; fp.vh = o + OFF_VH; fp.z_in = s.d_zin;
+            fp.mode = (a.mode == MODE_PROOF_AT_Z) ? 1 : 0;
+            fp.want_quotient = (a.mode == MODE_COMMIT_PROVE || a.mode == MODE_PROOF_AT_Z) ? 1 : 0;
+            fp.eval = (a.mode == MODE_POINT_ONLY) ? 0 : 1;
+            fp.nblobs = cnt; fp.out_x = o + OFF_X; fp.out_y = o + OFF_Y; fp.q_out = s.d_q; fp.bad = s.d_bad;
+            fp.out_stride = OUT_STRIDE;
+            timer_begin(d, d->s_main, T_FR);
+            k_fr_eval_quot<<<cnt, FR_THREADS, FR_SMEM_BYTES, d->s_main>>>(fp);
+            timer_end(d, d->s_main);
+            if (fp.want_quotient) {
+                launch_msm(d, s.d_q, cnt, s, nullptr, &splits);
+                timer_begin(d, d->s_main, T_FIN);
+                k_finalize<<<(cnt + 31) / 32, 32, 0, d->s_main>>>(s.d_partials, splits, cnt, s.d_bad, o + OFF_PROOF, nullptr,
+                                                                  o_stat, OUT_STRIDE);
+                timer_end(d, d->s_main);
+                k_status_only<<<(cnt + 127) / 128, 128, 0, d->s_main>>>(s.d_bad, cnt, o, o_stat, OUT_STRIDE, OFF_HASH);
+                d->stats.total_launches++;
+            } else {
+                k_status_only<<<(cnt + 127) / 128, 128, 0, d->s_main>>>(s.d_bad, cnt, o, o_stat, OUT_STRIDE, OFF_HASH);
+                d->stats.total_launches++;
+            }
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(s.ev_done, d->s_main));
+        // ---- output ----------------------------------------------------------------------
+        CUDA_TRY(cudaStreamWaitEvent(d->s_out, s.ev_done, 0));
+        if (a.outs_on_device) {
+            auto scatter = [&](uint8_t* dst, int off, int width) -> cudaError_t {
+                if (!dst) return cudaSuccess;
+                return cudaMemcpy2DAsync(dst + (size_t)width * first, width, o + off, OUT_STRIDE, width, (size_t)cnt,
+                                         cudaMemcpyDeviceToDevice, d->s_out);
+            };
+            CUDA_TRY(scatter(a.out_c, OFF_C, 48));
+            CUDA_TRY(scatter(a.out_vh, OFF_VH, 32));
+            CUDA_TRY(scatter(a.out_x, OFF_X, 32));
+            CUDA_TRY(scatter(a.out_y, OFF_Y, 32));
+            CUDA_TRY(scatter(a.out_proof, OFF_PROOF, 48));
+            if (a.status) CUDA_TRY(cudaMemcpyAsync(a.status + first, o_stat, (size_t)cnt, cudaMemcpyDeviceToDevice, d->s_out));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(s.h_out, o, (size_t)cnt * OUT_STRIDE, cudaMemcpyDeviceToHost, d->s_out));
+            CUDA_TRY(cudaMemcpyAsync(s.h_out + chunk * OUT_STRIDE, o_stat, (size_t)cnt, cudaMemcpyDeviceToHost, d->s_out));
+            d->stats.d2h_bytes += (uint64_t)cnt * (OUT_STRIDE + 1);
+        }
+        CUDA_TRY(cudaEventRecord(s.ev_out, d->s_out));
+    }
+    for (auto& s : d->slot) {
+        rk_status st = drain(s);
+        if (st != RK_OK) return st;
+    }
+    CUDA_TRY(cudaStreamSynchronize(d->s_main));
+    CUDA_TRY(cudaStreamSynchronize(d->s_sha));
+    CUDA_TRY(cudaStreamSynchronize(d->s_out));
+    timers_collect(d);
+    return RK_OK;
+}
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+rk_status run_batch(rk_kzg_ctx* ctx, BatchArgs a) {
+    if (!ctx) return fail(RK_ERR_ARG, "null context");
+    if (a.n == 0) return RK_OK;
+    if (!a.blobs) return fail(RK_ERR_ARG, "null blobs pointer");
+    cudaSetDevice(ctx->devs[0]->dev);
+    a.blobs_on_device = is_device_ptr(a.blobs);
+    uint8_t* outs[6] = {a.out_c, a.out_vh, a.out_x, a.out_y, a.out_proof, a.status};
+    int n_dev_out = 0, n_out = 0;
+    for (uint8_t* p : outs) if (p) { n_out++; n_dev_out += is_device_ptr(p) ? 1 : 0; }
+    if (n_dev_out != 0 && n_dev_out != n_out) return fail(RK_ERR_ARG, "outputs must be all host or all device pointers");
+    a.outs_on_device = n_dev_out != 0;
+    if ((a.blobs_on_device || a.outs_on_device) && ctx->devs.size() != 1)
+        return fail(RK_ERR_ARG, "device pointers need a single-device context");
+    if (a.blobs_on_device && ((uintptr_t)a.blobs & 15)) return fail(RK_ERR_ARG, "device blob pointer must be 16-byte aligned");
+    const size_t ndev = ctx->devs.size();
+    if (ndev == 1 || a.n < ndev) return run_shard(ctx->devs[0], a);
+    // contiguous shards, one host thread per device, host-side gather (no collective)
+    std::vector<rk_status> rc(ndev, RK_OK);
+    std::vector<std::string> msg(ndev);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < ndev; g++) {
+        const size_t lo = a.n * g / ndev, hi = a.n * (g + 1) / ndev;
+        BatchArgs s = a;
+        s.blobs = a.blobs + lo * BLOB_BYTES;
+        s.n = hi - lo;
+        if (a.zs) s.zs = a.zs + 32 * lo;
+        if (a.vhs) s.vhs = a.vhs + 32 * lo;
+        if (a.out_c) s.out_c = a.out_c + 48 * lo;
+        if (a.out_vh) s.out_vh = a.out_vh + 32 * lo;
+        if (a.out_x) s.out_x = a.out_x + 32 * lo;
+        if (a.out_y) s.out_y = a.out_y + 32 * lo;
+        if (a.out_proof) s.out_proof = a.out_proof + 48 * lo;
+        if (a.status) s.status = a.status + lo;
+        th.emplace_back([&, g, s]() { rc[g] = run_shard(ctx->devs[g], s); if (rc[g] != RK_OK) msg[g] = g_last_error; });
+    }
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < ndev; g++)
+        if (rc[g] != RK_OK) { g_last_error = msg[g]; return rc[g]; }
+    return RK_OK;
+}
+
+rk_status check_blob_len(size_t len) {
+    if (len != BLOB_BYTES) return fail(RK_ERR_BAD_LENGTH, "blob length %zu != %d", len, BLOB_BYTES);
+    return RK_OK;
+}
+
+}  // namespace
+
+// ========================================================================================
+// C ABI
+// ========================================================================================
+extern "C" {
+
+const char* rk_last_error(void) { return g_last_error.c_str(); }
+const char* rk_version(void) { return "raiko_b200-kzg 0.1 (sm_100a, 30-bit-limb IMAD.WIDE, fixed-base window table)"; }
+
+rk_status rk_kzg_ctx_create_ex(const uint8_t* settings, size_t len, const int* devices, int ndev, int window_bits,
+                               rk_kzg_ctx** out) {
+    if (!settings || !out) return fail(RK_ERR_ARG, "null argument");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(RK_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    std::vector<int> devs;
+    if (!devices || ndev <= 0) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        devs.push_back(cur);
+    } else {
+        for (int i = 0; i < ndev; i++) {
+            if (devices[i] < 0 || devices[i] >= count) return fail(RK_ERR_ARG, "device ordinal %d out of range", devices[i]);
+            devs.push_back(devices[i]);
+        }
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    auto* ctx = new rk_kzg_ctx;
+    std::vector<rk_status> rc(devs.size(), RK_OK);
+    std::vector<std::string> msg(devs.size());
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < devs.size(); i++) {
+        auto* d = new DeviceCtx;
+        d->dev = devs[i];
+        ctx->devs.push_back(d);
+    }
+    for (size_t i = 0; i < devs.size(); i++)
+        th.emplace_back([&, i]() {
+            rc[i] = init_device(ctx->devs[i], settings, len, window_bits, i == 0 ? &ctx->g2_be : nullptr);
+            if (rc[i] != RK_OK) msg[i] = g_last_error;
+        });
+    for (auto& t : th) t.join();
+    cudaSetDevice(prev);
+    for (size_t i = 0; i < devs.size(); i++)
+        if (rc[i] != RK_OK) {
+            g_last_error = msg[i];
+            rk_status st = rc[i];
+            rk_kzg_ctx_destroy(ctx);
+            return st;
+        }
+    ctx->geom = ctx->devs[0]->geom;
+    *out = ctx;
+    return RK_OK;
+}
+
+rk_status rk_kzg_ctx_create(const uint8_t* settings, size_t len, const int* devices, int ndev, rk_kzg_ctx** out) {
+    return rk_kzg_ctx_create_ex(settings, len, devices, ndev, 0, out);
+}
+
+void rk_kzg_ctx_destroy(rk_kzg_ctx* ctx) {
+    if (!ctx) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto* d : ctx->devs) free_device(d);
+    cudaSetDevice(prev);
+    delete ctx;
+}
+
+int rk_kzg_ctx_window_bits(const rk_kzg_ctx* ctx) { return ctx ? ctx->geom.c : 0; }
+int rk_kzg_ctx_num_devices(const rk_kzg_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+uint64_t rk_kzg_ctx_table_bytes(const rk_kzg_ctx* ctx) { return ctx ? ctx->devs[0]->table_bytes : 0; }
+
+rk_status rk_kzg_ctx_export_settings(rk_kzg_ctx* ctx, int kind, uint8_t* out, size_t* len) {
+    if (!ctx || !out || !len) return fail(RK_ERR_ARG, "null argument");
+    const size_t need = kind == 0 ? RAW_LEN : kind == 1 ? BINCODE_LEN : 0;
+    if (!need) return fail(RK_ERR_ARG, "kind must be 0 (raw) or 1 (bincode)");
+    if (*len < need) { *len = need; return fail(RK_ERR_BAD_LENGTH, "output buffer too small, need %zu", need); }
+    DeviceCtx* d = ctx->devs[0];
+    std::lock_guard<std::mutex> lock(d->mu);
+    CUDA_TRY(cudaSetDevice(d->dev));
+    uint8_t* d_buf = nullptr;
+    const size_t g1b = 144ull * NPTS, g2b = 288ull * N_G2, rb = 32ull * 4097;
+    CUDA_TRY(cudaMalloc(&d_buf, g1b + g2b + 3 * rb + 192 * N_G2));
+    uint8_t *d_g1 = d_buf, *d_g2 = d_buf + g1b, *d_r0 = d_g2 + g2b, *d_r1 = d_r0 + rb, *d_r2 = d_r1 + rb, *d_g2in = d_r2 + rb;
+    k_setup_to_ref<<<NPTS / 64, 64>>>(d->g1_aff, NPTS, d_g1);
+    // G2: x.c0 x.c1 y.c0 y.c1 (BE) -> 6 Montgomery coordinates with Z = (1, 0)
+    std::vector<uint8_t> g2six(288 * N_G2, 0);
+    for (int i = 0; i < N_G2; i++) {
+        memcpy(g2six.data() + 288 * i, ctx->g2_be.data() + 192 * i, 192);
+        g2six[288 * i + 4 * 48 + 47] = 1;
+    }
+    uint8_t* d_g2be = nullptr;
+    CUDA_TRY(cudaMalloc(&d_g2be, g2six.size()));
+    CUDA_TRY(cudaMemcpy(d_g2be, g2six.data(), g2six.size(), cudaMemcpyHostToDevice));
+    k_fp_be_to_ref<<<(6 * N_G2 + 63) / 64, 64>>>(d_g2be, 6 * N_G2, d_g2);
+    k_roots_export<<<(4097 + 63) / 64, 64>>>(0, 4097, d_r0);
+    k_roots_export<<<(4097 + 63) / 64, 64>>>(1, 4097, d_r1);
+    k_roots_export<<<(4096 + 63) / 64, 64>>>(2, 4096, d_r2);
+    (void)d_g2in;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<uint8_t> h(g1b + g2b + 3 * rb);
+    CUDA_TRY(cudaMemcpy(h.data(), d_buf, h.size(), cudaMemcpyDeviceToHost));
+    cudaFree(d_buf); cudaFree(d_g2be);
+    const uint8_t *h_g1 = h.data(), *h_g2 = h.data() + g1b, *h_r0 = h_g2 + g2b, *h_r1 = h_r0 + rb, *h_r2 = h_r1 + rb;
+    memset(out, 0, need);
+    auto put_le64 = [&](size_t off, uint64_t v) { memcpy(out + off, &v, 8); };
+    if (kind == 0) {
+        out[6] = 0x10;                                   // max_width = 4096, big-endian u64
+        memcpy(out + RAW_ROOTS, h_r2, 32 * 4096);
+        memcpy(out + RAW_G1, h_g1, g1b);
+        memcpy(out + RAW_G2, h_g2, g2b);
+    } else {
+        put_le64(0, 4096);
+        memcpy(out + 8, h_r0 + 32, 32);                  // root_of_unity = w^1
+        put_le64(BC_EXPANDED, 4097); memcpy(out + BC_EXPANDED + 8, h_r0, rb);
+        put_le64(BC_REVERSE, 4097);  memcpy(out + BC_REVERSE + 8, h_r1, rb);
+        put_le64(BC_ROOTS, 4096);    memcpy(out + BC_ROOTS + 8, h_r2, 32 * 4096);
+        put_le64(BC_G1, 4096);       memcpy(out + BC_G1 + 8, h_g1, g1b);
+        put_le64(BC_G2, N_G2);       memcpy(out + BC_G2 + 8, h_g2, g2b);
+        out[BINCODE_LEN - 1] = 0;                        // precomputation: None
+    }
+    *len = need;
+    return RK_OK;
+}
+
+rk_status rk_kzg_to_versioned_hash(const uint8_t commitment[48], uint8_t out_hash[32]) {
+    if (!commitment || !out_hash) return fail(RK_ERR_ARG, "null argument");
+    sha256_short(commitment, 48, out_hash);
+    out_hash[0] = RK_VERSIONED_HASH_VERSION_KZG;
+    return RK_OK;
+}
+
+rk_status rk_commit_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_t n, uint8_t* out_commitments,
+                          uint8_t* out_versioned_hashes, uint8_t* per_blob_status) {
+    if (!out_commitments) return fail(RK_ERR_ARG, "out_commitments is required");
+    BatchArgs a{};
+    a.mode = MODE_COMMIT; a.blobs = blobs; a.n = n;
+    a.out_c = out_commitments; a.out_vh = out_versioned_hashes; a.status = per_blob_status;
+    return run_batch(ctx, a);
+}
+
+rk_status rk_commit_prove_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_t n, uint8_t* out_commitments,
+                                uint8_t* out_versioned_hashes, uint8_t* out_x, uint8_t* out_y, uint8_t* out_proofs,
+                                uint8_t* per_blob_status) {
+    if (!out_commitments) return fail(RK_ERR_ARG, "out_commitments is required");
+    BatchArgs a{};
+    a.mode = MODE_COMMIT_PROVE; a.blobs = blobs; a.n = n;
+    a.out_c = out_commitments; a.out_vh = out_versioned_hashes; a.out_x = out_x; a.out_y = out_y;
+    a.out_proof = out_proofs; a.status = per_blob_status;
+    return run_batch(ctx, a);
+}
+
+rk_status rk_compute_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* zs, size_t n,
+                                     uint8_t* out_proofs, uint8_t* out_y, uint8_t* per_blob_status) {
+    if (!out_proofs || !zs) return fail(RK_ERR_ARG, "zs and out_proofs are required");
+    if (is_device_ptr(zs)) return fail(RK_ERR_ARG, "zs must be a host pointer");
+    BatchArgs a{};
+    a.mode = MODE_PROOF_AT_Z; a.blobs = blobs; a.zs = zs; a.n = n;
+    a.out_proof = out_proofs; a.out_y = out_y; a.status = per_blob_status;
+    return run_batch(ctx, a);
+}
+
+static rk_status single_status(uint8_t st) {
+    if (st == 0) return RK_OK;
+    return fail((rk_status)st, "Failed to deserialize blob to field elements");
+}
+
+rk_status rk_blob_to_kzg_commitment(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, uint8_t out_commitment[48]) {
+    rk_status st = check_blob_len(blob_len);
+    if (st != RK_OK) return st;
+    uint8_t c[48], s = 0;
+    st = rk_commit_batch(ctx, blob, 1, c, nullptr, &s);
+    if (st != RK_OK) return st;
+    if (s) return single_status(s);
+    memcpy(out_commitment, c, 48);
+    return RK_OK;
+}
+
+rk_status rk_get_evaluation_point(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, const uint8_t versioned_hash[32],
+                                  uint8_t out_x[32]) {
+    rk_status st = check_blob_len(blob_len);
+    if (st != RK_OK) return st;
+    if (!versioned_hash || !out_x) return fail(RK_ERR_ARG, "null argument");
+    BatchArgs a{};
+    a.mode = MODE_POINT_ONLY; a.blobs = blob; a.vhs = versioned_hash; a.n = 1; a.out_x = out_x;
+    return run_batch(ctx, a);   // no deserialisation on this path in the reference either
+}
+
+rk_status rk_proof_of_equivalence(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, const uint8_t versioned_hash[32],
+                                  uint8_t out_x[32], uint8_t out_y[32]) {
+    rk_status st = check_blob_len(blob_len);
+    if (st != RK_OK) return st;
+    if (!versioned_hash || !out_x || !out_y) return fail(RK_ERR_ARG, "null argument");
+    uint8_t x[32], y[32], s = 0;
+    BatchArgs a{};
+    a.mode = MODE_EVAL_ONLY; a.blobs = blob; a.vhs = versioned_hash; a.n = 1; a.out_x = x; a.out_y = y; a.status = &s;
+    st = run_batch(ctx, a);
+    if (st != RK_OK) return st;
+    if (s) return single_status(s);
+    memcpy(out_x, x, 32); memcpy(out_y, y, 32);
+    return RK_OK;
+}
+
+rk_status rk_compute_kzg_proof(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, const uint8_t z[32],
+                               uint8_t out_proof[48], uint8_t out_y[32]) {
+    rk_status st = check_blob_len(blob_len);
+    if (st != RK_OK) return st;
+    if (!z || !out_proof) return fail(RK_ERR_ARG, "null argument");
+    uint8_t p[48], y[32], s = 0;
+    st = rk_compute_kzg_proof_batch(ctx, blob, z, 1, p, y, &s);
+    if (st != RK_OK) return st;
+    if (s) return single_status(s);
+    memcpy(out_proof, p, 48);
+    if (out_y) memcpy(out_y, y, 32);
+    return RK_OK;
+}
+
+rk_status rk_calc_kzg_proof(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, const uint8_t versioned_hash[32],
+                            uint8_t out_proof[48]) {
+    uint8_t x[32];
+    rk_status st = rk_get_evaluation_point(ctx, blob, blob_len, versioned_hash, x);
+    if (st != RK_OK) return st;
+    return rk_compute_kzg_proof(ctx, blob, blob_len, x, out_proof, nullptr);
+}
+
+void rk_kzg_stats_enable(rk_kzg_ctx* ctx, int enable) {
+    if (ctx) for (auto* d : ctx->devs) d->stats_on = enable != 0;
+}
+void rk_kzg_stats_reset(rk_kzg_ctx* ctx) {
+    if (ctx) for (auto* d : ctx->devs) { std::lock_guard<std::mutex> l(d->mu); d->stats = rk_kzg_stats{}; }
+}
+void rk_kzg_stats_get(rk_kzg_ctx* ctx, rk_kzg_stats* out) {
+    if (!ctx || !out) return;
+    *out = rk_kzg_stats{};
+    for (auto* d : ctx->devs) {
+        std::lock_guard<std::mutex> l(d->mu);
+        out->msm_ms += d->stats.msm_ms; out->fr_ms += d->stats.fr_ms; out->sha_ms += d->stats.sha_ms;
+        out->finalize_ms += d->stats.finalize_ms; out->msm_launches += d->stats.msm_launches;
+        out->total_launches += d->stats.total_launches; out->h2d_bytes += d->stats.h2d_bytes;
+        out->d2h_bytes += d->stats.d2h_bytes; out->msm_point_adds += d->stats.msm_point_adds;
+    }
+}
+
+rk_status rk_measure_imad_peak(int device, double* out_macs_per_sec, double* out_sm_clock_mhz) {
+    if (!out_macs_per_sec) return fail(RK_ERR_ARG, "null argument");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+        return fail(RK_ERR_CUDA, "no such CUDA device %d", device);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 8192;
+    uint64_t* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(uint64_t) * blocks * 256));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0);
+        k_imad_peak<<<blocks, 256>>>(d_out, 3, iters);
+        cudaEventRecord(e1);
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *out_macs_per_sec = (double)blocks * 256 * iters * 16 * 8 / (best * 1e-3);
+    if (out_sm_clock_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        *out_sm_clock_mhz = khz / 1000.0;
+    }
+    cudaSetDevice(prev);
+    return RK_OK;
+}
+
+}  // extern "C"

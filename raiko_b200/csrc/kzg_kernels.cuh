@@ -1,0 +1,719 @@
+// Device kernels of the blob-KZG path (sm_100a).
+//
+//   k_msm            fixed-base MSM over the precomputed window table (hot kernel)
+//   k_finalize       partial sums -> affine -> 48-byte compressed G1 (+ versioned hash)
+//   k_sha_blob       sha256(blob), one chain per thread
+//   k_fr_eval_quot   raiko challenge, barycentric evaluation, quotient in evaluation form
+//   k_setup_* / k_table_*   trusted-setup decoding and window-table construction
+//
+// Reference semantics: lib/src/primitives/eip4844.rs:44-99 (wrapper) and the
+// rust-kzg algorithms it calls.
+#pragma once
+#include <cuda_runtime.h>
+#include "g1.cuh"
+#include "sha256.cuh"
+
+namespace rk {
+
+constexpr int NPTS = 4096;             // FIELD_ELEMENTS_PER_BLOB
+constexpr int BLOB_BYTES = 131072;
+
+// ---------------------------------------------------------------------------
+// Window-table geometry.
+//
+// Scalars (< r < 2^255) are recoded into W = ceil(255 / c) base-2^c digits.  Digits
+// 0..W-2 are signed, |d| <= 2^(c-1); the top digit stays unsigned (it absorbs the last
+// carry and is bounded by (r >> c(W-1)) + 1).  The table holds EVERY multiple a digit
+// can select:  T[i][j][k] = (k+1) * 2^(c j) * L_i  in affine Montgomery form, so one
+// blob's MSM is exactly 4096 * W mixed additions and there is no bucket-reduction
+// phase at all -- the per-blob buckets of Pippenger's method are pre-aggregated
+// into HBM once (c = 15: 291 822 entries per point, 114.7 GB).
+// ---------------------------------------------------------------------------
+struct TableGeom {
+    int c;                 // window bits (4..15)
+    int W;                 // windows
+    uint32_t half;         // 2^(c-1) entries per signed window
+    uint32_t top_entries;  // entries of the unsigned top window
+    uint32_t per_point;    // (W-1)*half + top_entries
+};
+
+struct alignas(16) TableEntry {        // 96 bytes: three 32-byte sectors
+    uint32_t x[12];
+    uint32_t y[12];
+};
+
+__device__ __forceinline__ uint4 ldg_nc(const uint4* p) { return __ldg(p); }
+
+// ---------------------------------------------------------------------------
+// Hot kernel: one warp per (blob, split).  Lane l of the warp owns points
+// split*PW + 32 t + l; for each it walks the W digits, fetches the selected table
+// entry (random 96-byte read, software-prefetched one addition ahead) and adds it
+// to a register-resident XYZZ accumulator.  Lanes are then combined with shuffles.
+// ---------------------------------------------------------------------------
+struct MsmParams {
+    const TableEntry* table;
+    TableGeom g;
+    const uint8_t* scalars;   // nblobs * 131072 bytes, 32-byte big-endian scalars
+    int nblobs;
+    int splits_log2;          // warps per blob = 1 << splits_log2  (<= 128)
+    G1Xyzz* partials;         // nblobs << splits_log2
+    uint32_t* bad;            // per blob: set non-zero when a scalar is >= r (may be null)
+};
+
+__device__ __forceinline__ void shfl_fp(Fp& r, const Fp& a, int delta) {
+#pragma unroll
+    for (int i = 0; i < FP_N; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], delta);
+}
+
+__device__ __forceinline__ bool scalar_geq_r(const uint32_t (&s)[8]) {
+    for (int k = 7; k >= 0; k--) {
+        uint32_t m = FR_MOD_W32::at(k);
+        if (s[k] > m) return true;
+        if (s[k] < m) return false;
+    }
+    return true;
+}
+
+// 32 big-endian bytes at p (16-byte aligned) -> little-endian words
+__device__ __forceinline__ void load_scalar_be(uint32_t (&s)[8], const uint8_t* p) {
+    uint4 hi = ldg_nc(reinterpret_cast<const uint4*>(p));
+    uint4 lo = ldg_nc(reinterpret_cast<const uint4*>(p) + 1);
+    s[7] = __byte_perm(hi.x, 0, 0x0123); s[6] = __byte_perm(hi.y, 0, 0x0123);
+    s[5] = __byte_perm(hi.z, 0, 0x0123); s[4] = __byte_perm(hi.w, 0, 0x0123);
+    s[3] = __byte_perm(lo.x, 0, 0x0123); s[2] = __byte_perm(lo.y, 0, 0x0123);
+    s[1] = __byte_perm(lo.z, 0, 0x0123); s[0] = __byte_perm(lo.w, 0, 0x0123);
+}
+
+__global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int blob = warp >> prm.splits_log2;
+    if (blob >= prm.nblobs) return;
+    const int split = warp & ((1 << prm.splits_log2) - 1);
+    const int pts_per_warp = NPTS >> prm.splits_log2;
+    const int per_lane = pts_per_warp >> 5;
+    const int c = prm.g.c, W = prm.g.W;
+    const uint32_t half = prm.g.half, cmask = (1u << c) - 1u;
+    const uint8_t* sc = prm.scalars + (size_t)blob * BLOB_BYTES;
+    const int first_pt = split * pts_per_warp + lane;
+
+    G1Xyzz acc;
+    g1_set_inf(acc);
+
+    uint4 cur[6];
+    int cur_kind = 0;                    // 0 none, 1 add, 2 add negated
+    uint32_t s[8];
+    uint32_t carry = 0;
+    int t = 0, j = 0;
+    const TableEntry* pbase = nullptr;
+    bool any_bad = false;
+    const int total = per_lane * W;
+
+    for (int it = 0; it <= total; it++) {
+        uint4 nxt[6];
+        int nxt_kind = 0;
+        if (it < total) {
+            if (j == 0) {
+                const int pt = first_pt + 32 * t;
+                load_scalar_be(s, sc + 32 * pt);
+                any_bad |= scalar_geq_r(s);
+                carry = 0;
+                pbase = prm.table + (size_t)pt * prm.g.per_point;
+            }
+            uint32_t raw, idx;
+            bool neg = false;
+            if (j < W - 1) {
+                raw = (s[0] & cmask) + carry;
+#pragma unroll
+                for (int k = 0; k < 7; k++) s[k] = __funnelshift_r(s[k], s[k + 1], c);
+                s[7] >>= c;
+                if (raw > half) { idx = (1u << c) - raw; neg = true; carry = 1; }
+                else { idx = raw; carry = 0; }
+            } else {
+                idx = s[0] + carry;
+            }
+            if (idx != 0) {
+                const uint4* e = reinterpret_cast<const uint4*>(pbase + ((size_t)j * half + (idx - 1)));
+#pragma unroll
+                for (int k = 0; k < 6; k++) nxt[k] = ldg_nc(e + k);
+                nxt_kind = neg ? 2 : 1;
+            }
+            if (++j == W) { j = 0; t++; }
+        }
+        if (cur_kind) {
+            uint32_t w[24];
+#pragma unroll
+            for (int k = 0; k < 6; k++) { w[4 * k] = cur[k].x; w[4 * k + 1] = cur[k].y; w[4 * k + 2] = cur[k].z; w[4 * k + 3] = cur[k].w; }
+            Fp x2, y2;
+            fe_unpack<FpTag>(x2, w);
+            fe_unpack<FpTag>(y2, w + 12);
+            if (cur_kind == 2) fe_neg<FpTag, 2>(y2, y2);
+            g1_madd(acc, x2, y2);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) cur[k] = nxt[k];
+        cur_kind = nxt_kind;
+    }
+
+    if (prm.bad != nullptr && __any_sync(0xffffffffu, any_bad) && lane == 0) atomicOr(prm.bad + blob, 1u);
+
+    // combine the 32 lane sums
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+        G1Xyzz o;
+        shfl_fp(o.x, acc.x, delta); shfl_fp(o.y, acc.y, delta);
+        shfl_fp(o.zz, acc.zz, delta); shfl_fp(o.zzz, acc.zzz, delta);
+        if (lane < delta) g1_add(acc, o);
+    }
+    if (lane == 0) prm.partials[warp] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// k_finalize: one thread per blob.  Sums the blob's partial sums, converts to affine
+// (one Fermat inversion), writes the 48-byte compressed point, and optionally the
+// versioned hash  sha256(commitment) with byte 0 = 0x01  (eip4844.rs:91-95).
+// A blob flagged `bad` (non-canonical field element; Eip4844Error::DeserializeBlob)
+// gets zeroed outputs and status RK_ERR_NONCANONICAL_FE (= 2).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_finalize(const G1Xyzz* partials, int splits, int nblobs,
+                                                  const uint32_t* bad, uint8_t* out_g1,
+                                                  uint8_t* out_vh, uint8_t* status, int stride) {
+    const int blob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blob >= nblobs) return;
+    uint8_t* o = out_g1 + (size_t)stride * blob;
+    if (bad != nullptr && bad[blob]) {
+        for (int i = 0; i < 48; i++) o[i] = 0;
+        if (out_vh) for (int i = 0; i < 32; i++) out_vh[(size_t)stride * blob + i] = 0;
+        if (status) status[blob] = 2;
+        return;
+    }
+    G1Xyzz acc = partials[(size_t)blob * splits];
+    for (int s = 1; s < splits; s++) {
+        G1Xyzz p = partials[(size_t)blob * splits + s];
+        g1_add(acc, p);
+    }
+    uint8_t buf[48];
+    g1_compress(buf, acc);
+    for (int i = 0; i < 48; i++) o[i] = buf[i];
+    if (out_vh) {
+        uint8_t h[32];
+        sha256_short(buf, 48, h);
+        h[0] = 0x01;
+        for (int i = 0; i < 32; i++) out_vh[(size_t)stride * blob + i] = h[i];
+    }
+}
+
+// Blobs that failed deserialisation: zero every output of the record, set status 2.
+__global__ void k_status_only(const uint32_t* bad, int nblobs, uint8_t* rec, uint8_t* status, int stride, int zero_bytes) {
+    const int blob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blob >= nblobs || !bad[blob]) return;
+    for (int i = 0; i < zero_bytes; i++) rec[(size_t)stride * blob + i] = 0;
+    status[blob] = 2;
+}
+
+// ---------------------------------------------------------------------------
+// k_sha_blob: sha256 over each 131072-byte blob (first half of get_evaluation_point,
+// eip4844.rs:45).  One thread per blob: 2048 data blocks + one padding block.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_sha_blob(const uint8_t* blobs, int nblobs, uint8_t* out_hash, int stride) {
+    const int blob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blob >= nblobs) return;
+    const uint4* p = reinterpret_cast<const uint4*>(blobs + (size_t)blob * BLOB_BYTES);
+    Sha256State st;
+    sha256_init(st);
+    for (int b = 0; b < BLOB_BYTES / 64; b++) {
+        uint32_t w[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint4 v = ldg_nc(p + 4 * b + q);
+            w[4 * q] = __byte_perm(v.x, 0, 0x0123); w[4 * q + 1] = __byte_perm(v.y, 0, 0x0123);
+            w[4 * q + 2] = __byte_perm(v.z, 0, 0x0123); w[4 * q + 3] = __byte_perm(v.w, 0, 0x0123);
+        }
+        sha256_compress(st, w);
+    }
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = 0;
+    w[0] = 0x80000000u;
+    w[15] = (uint32_t)BLOB_BYTES * 8u;
+    sha256_compress(st, w);
+    uint8_t* o = out_hash + (size_t)stride * blob;
+    for (int i = 0; i < 8; i++) store_be32(o + 4 * i, st.h[i]);
+}
+
+// ---------------------------------------------------------------------------
+// k_fr_eval_quot: one CTA (256 threads) per blob, 16 field elements per thread.
+//
+//   z   = hash_to_bls_field(sha256(blob_hash || vh))      (eip4844.rs:44-48)  [mode 0]
+//         or the caller's z reduced mod r                                    [mode 1]
+//   y   = p(z), barycentric over the bit-reversed domain   (App. B.3)
+//   q_i = (p_i - y) / (w_i - z), with the z-in-domain case (App. B.4)
+//
+// A single CTA-wide Montgomery batch inversion of (z - w_i) serves both y and q
+// (the reference inverts twice; the values are identical).  Inverses live in shared
+// memory (4096 x 36 B).  q is written in the blob's own wire format (32-byte
+// big-endian canonical scalars) so the same k_msm consumes it.
+// ---------------------------------------------------------------------------
+struct FrParams {
+    const uint8_t* blobs;       // nblobs * 131072
+    const Fr* roots_brp;        // 4096 Montgomery
+    const uint8_t* blob_hash;   // 32 bytes per blob at out_stride (mode 0)
+    const uint8_t* vh;          // 32 bytes per blob at out_stride (mode 0)
+    const uint8_t* z_in;        // nblobs * 32, dense (mode 1)
+    int mode;
+    int want_quotient;
+    int eval;                   // 0: only the challenge x is wanted (get_evaluation_point)
+    int nblobs;
+    int out_stride;             // byte stride of the per-blob output record
+    uint8_t* out_x;             // 32 bytes per blob at out_stride (may be null)
+    uint8_t* out_y;             // 32 bytes per blob at out_stride (may be null)
+    uint8_t* q_out;             // nblobs * 131072 (when want_quotient)
+    uint32_t* bad;              // per blob: set when a field element is >= r
+};
+
+__device__ __forceinline__ void fr_load_be(Fr& canon, bool& geq_r, const uint8_t* p) {
+    uint32_t s[8];
+    load_scalar_be(s, p);
+    geq_r = scalar_geq_r(s);
+    fe_unpack<FrTag>(canon, s);
+}
+__device__ __forceinline__ void fr_store_be(uint8_t* p, const Fr& canon) {
+    uint32_t w[8];
+    fe_pack<FrTag>(w, canon);
+    uint4 hi, lo;
+    hi.x = __byte_perm(w[7], 0, 0x0123); hi.y = __byte_perm(w[6], 0, 0x0123);
+    hi.z = __byte_perm(w[5], 0, 0x0123); hi.w = __byte_perm(w[4], 0, 0x0123);
+    lo.x = __byte_perm(w[3], 0, 0x0123); lo.y = __byte_perm(w[2], 0, 0x0123);
+    lo.z = __byte_perm(w[1], 0, 0x0123); lo.w = __byte_perm(w[0], 0, 0x0123);
+    reinterpret_cast<uint4*>(p)[0] = hi;
+    reinterpret_cast<uint4*>(p)[1] = lo;
+}
+// 32 big-endian bytes -> value mod r (value < 2^256 < 3r) -> Montgomery
+__device__ __forceinline__ void fr_from_be_reduce(Fr& mont, Fr& canon, const uint8_t* p) {
+    uint32_t s[8];
+    for (int k = 0; k < 8; k++) s[7 - k] = load_be32(p + 4 * k);
+    fe_unpack<FrTag>(canon, s);
+    fe_cond_sub_mod<FrTag>(canon);
+    fe_cond_sub_mod<FrTag>(canon);
+    fe_to_mont(mont, canon);
+}
+
+constexpr int FR_THREADS = 256;
+constexpr int FR_PER_THREAD = NPTS / FR_THREADS;   // 16
+
+__global__ void __launch_bounds__(FR_THREADS) k_fr_eval_quot(FrParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Fr* inv_s = reinterpret_cast<Fr*>(smem_raw);            // [4096] prefix products, then inverses
+    Fr* tot_s = inv_s + NPTS;                                // [256] per-thread totals -> inverses
+    Fr* lane_s = tot_s + FR_THREADS;                         // [32]
+    Fr* bc_s = lane_s + 32;                                  // [4] broadcast: z, y, scale, zinv
+    __shared__ int s_m;                                      // index with w_m == z, or -1
+    __shared__ int s_bad;
+
+    const int tid = threadIdx.x;
+    const int blob = blockIdx.x;
+    const uint8_t* bp = prm.blobs + (size_t)blob * BLOB_BYTES;
+
+    if (tid == 0) {
+        s_m = -1;
+        s_bad = 0;
+        Fr zc, zm;
+        if (prm.mode == 0) {
+            uint8_t buf[64], h[32];
+            for (int i = 0; i < 32; i++) { buf[i] = prm.blob_hash[(size_t)prm.out_stride * blob + i]; buf[32 + i] = prm.vh[(size_t)prm.out_stride * blob + i]; }
+            sha256_short(buf, 64, h);
+            fr_from_be_reduce(zm, zc, h);
+        } else {
+            fr_from_be_reduce(zm, zc, prm.z_in + 32 * (size_t)blob);
+        }
+        bc_s[0] = zm;
+        if (prm.out_x) {
+            uint8_t* ox = prm.out_x + (size_t)prm.out_stride * blob;
+            uint32_t w[8];
+            fe_pack<FrTag>(w, zc);
+            for (int k = 0; k < 8; k++) store_be32(ox + 4 * k, w[7 - k]);
+        }
+    }
+    __syncthreads();
+    if (!prm.eval) return;
+    const Fr z = bc_s[0];
+
+    // ---- phase A: d_i = z - w_i, exclusive prefix products per thread -----------------
+    Fr run;
+    fe_const<FrTag, FR_ONE>(run);
+    for (int k = 0; k < FR_PER_THREAD; k++) {
+        const int i = k * FR_THREADS + tid;   // interleaved: coalesced loads, conflict-free smem
+        Fr w = prm.roots_brp[i], d;
+        fe_sub<FrTag, 2>(d, z, w);                 // < 4r
+        inv_s[i] = run;
+        if (fe_is_zero_mod(d)) { s_m = i; }        // at most one i can match
+        else fe_mul(run, run, d);
+    }
+    tot_s[tid] = run;
+    __syncthreads();
+
+    // ---- phase B: invert the 256 thread totals (warp 0: 32 lanes x 8, then lane 0) ----
+    if (tid < 32) {
+        Fr pre[8], lrun;
+        fe_const<FrTag, FR_ONE>(lrun);
+        for (int k = 0; k < 8; k++) { pre[k] = lrun; fe_mul(lrun, lrun, tot_s[tid * 8 + k]); }
+        lane_s[tid] = lrun;
+        __syncwarp();
+        if (tid == 0) {
+            Fr lpre[32], g;
+            fe_const<FrTag, FR_ONE>(g);
+            for (int l = 0; l < 32; l++) { lpre[l] = g; fe_mul(g, g, lane_s[l]); }
+            Fr ginv;
+            fe_inv(ginv, g);
+            for (int l = 31; l >= 0; l--) {
+                Fr li;
+                fe_mul(li, ginv, lpre[l]);
+                fe_mul(ginv, ginv, lane_s[l]);
+                lane_s[l] = li;
+            }
+        }
+        __syncwarp();
+        Fr linv = lane_s[tid];
+        for (int k = 7; k >= 0; k--) {
+            Fr ti, tv = tot_s[tid * 8 + k];
+            fe_mul(ti, linv, pre[k]);
+            fe_mul(linv, linv, tv);
+            tot_s[tid * 8 + k] = ti;
+        }
+    }
+    __syncthreads();
+    const int m = s_m;
+
+    // ---- phase C: per-element inverses, partial sum for y ------------------------------
+    Fr inv_run = tot_s[tid];
+    Fr sum;
+    fe_zero(sum);
+    bool bad = false;
+    for (int k = FR_PER_THREAD - 1; k >= 0; k--) {
+        const int i = k * FR_THREADS + tid;   // interleaved: coalesced loads, conflict-free smem
+        Fr w = prm.roots_brp[i], d, inv_i;
+        fe_sub<FrTag, 2>(d, z, w);
+        if (i == m) {
+            fe_zero(inv_i);                            // slot unused
+        } else {
+            Fr pre = inv_s[i];
+            fe_mul(inv_i, inv_run, pre);
+            fe_mul(inv_run, inv_run, d);
+        }
+        inv_s[i] = inv_i;
+        Fr pc, pm, t;
+        bool g;
+        fr_load_be(pc, g, bp + 32 * i);
+        bad |= g;
+        fe_to_mont(pm, pc);
+        fe_mul(t, pm, w);
+        fe_mul(t, t, inv_i);
+        fe_add(sum, sum, t);                           // < 4096 * 1.1 r, fits 270 bits
+    }
+    if (bad) s_bad = 1;
+    // CTA reduction of `sum` through shared memory (reuse tot_s)
+    __syncthreads();
+    tot_s[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        Fr y, total;
+        fe_zero(total);
+        for (int k = 0; k < FR_THREADS; k++) fe_add(total, total, tot_s[k]);
+        if (m >= 0) {
+            Fr pc; bool g;
+            fr_load_be(pc, g, bp + 32 * m);
+            fe_to_mont(y, pc);
+        } else {
+            Fr zp = z, one, scale;
+            for (int k = 0; k < 12; k++) fe_sqr(zp, zp);          // z^4096
+            fe_const<FrTag, FR_ONE>(one);
+            fe_sub<FrTag, 2>(zp, zp, one);
+            fe_const<FrTag, FR_INV4096>(scale);
+            fe_mul(zp, zp, scale);
+            fe_mul(y, total, zp);
+        }
+        bc_s[1] = y;
+        if (prm.out_y) {
+            Fr yc;
+            fe_from_mont(yc, y);
+            uint8_t* oy = prm.out_y + (size_t)prm.out_stride * blob;
+            uint32_t w[8];
+            fe_pack<FrTag>(w, yc);
+            for (int k = 0; k < 8; k++) store_be32(oy + 4 * k, w[7 - k]);
+        }
+        if (s_bad && prm.bad) atomicOr(prm.bad + blob, 1u);
+    }
+    __syncthreads();
+    if (!prm.want_quotient) return;
+    const Fr y = bc_s[1];
+    uint8_t* qp = prm.q_out + (size_t)blob * BLOB_BYTES;
+
+    // ---- phase D: q_i = (y - p_i) * 1/(z - w_i) ----------------------------------------
+    Fr sum_m;
+    fe_zero(sum_m);
+    for (int k = 0; k < FR_PER_THREAD; k++) {
+        const int i = k * FR_THREADS + tid;   // interleaved: coalesced loads, conflict-free smem
+        if (i == m) continue;
+        Fr pc, pm, t, q, qc;
+        bool g;
+        fr_load_be(pc, g, bp + 32 * i);
+        fe_to_mont(pm, pc);
+        fe_sub<FrTag, 2>(t, y, pm);                    // y - p_i  (< 4r)
+        Fr inv_i = inv_s[i];
+        fe_mul(q, t, inv_i);
+        fe_from_mont(qc, q);
+        fr_store_be(qp + 32 * i, qc);
+        if (m >= 0) {
+            // q_m = sum_{i != m} (p_i - y) w_i / (z (z - w_i)) = -(1/z) sum q_i w_i   (App. B.4)
+            Fr w = prm.roots_brp[i];
+            fe_mul(t, q, w);
+            fe_add(sum_m, sum_m, t);
+        }
+    }
+    if (m >= 0) {                                      // uniform per CTA
+        __syncthreads();
+        tot_s[tid] = sum_m;
+        __syncthreads();
+        if (tid == 0) {
+            Fr total, zinv, qm, qc;
+            fe_zero(total);
+            for (int k = 0; k < FR_THREADS; k++) fe_add(total, total, tot_s[k]);
+            fe_inv(zinv, z);
+            fe_mul(qm, total, zinv);
+            fe_neg<FrTag, 2>(qm, qm);
+            fe_from_mont(qc, qm);
+            fr_store_be(qp + 32 * m, qc);
+        }
+    }
+}
+constexpr size_t FR_SMEM_BYTES = sizeof(Fr) * (NPTS + FR_THREADS + 32 + 4);
+
+// ---------------------------------------------------------------------------
+// Trusted-setup decoding
+// ---------------------------------------------------------------------------
+// compressed 48-byte points -> affine Montgomery.  err[0] = first failing index + 1.
+__global__ void k_setup_decompress(const uint8_t* in, int n, G1Affine* out, int* err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine a;
+    int rc = g1_decompress(a, in + 48 * (size_t)i);
+    if (rc != 0) { atomicCAS(err, 0, i + 1); return; }     // infinity is not a valid setup point either
+    out[i] = a;
+}
+// reference layout: X | Y | Z as Montgomery (R = 2^384) little-endian limbs, Z must be 1
+__global__ void k_setup_from_ref(const uint8_t* in, int n, G1Affine* out, int* err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(in + 144 * (size_t)i);
+    uint32_t xw[12], yw[12], zw[12];
+    for (int k = 0; k < 12; k++) { xw[k] = w[k]; yw[k] = w[12 + k]; zw[k] = w[24 + k]; }
+    Fp x, y, z, conv, one, t;
+    fe_unpack<FpTag>(x, xw); fe_unpack<FpTag>(y, yw); fe_unpack<FpTag>(z, zw);
+    fe_const<FpTag, FP_FROM_REF>(conv);
+    fe_mul(x, x, conv); fe_mul(y, y, conv); fe_mul(z, z, conv);
+    fe_const<FpTag, FP_ONE>(one);
+    fe_sub<FpTag, 2>(t, z, one);
+    bool ok = fe_is_zero_mod(t);
+    // on curve: y^2 = x^3 + 4
+    Fp lhs, rhs, b4;
+    fe_sqr(lhs, y);
+    fe_sqr(rhs, x); fe_mul(rhs, rhs, x);
+    fe_const<FpTag, FP_B_COEFF>(b4);
+    fe_add(rhs, rhs, b4);
+    fe_sub<FpTag, 4>(t, lhs, rhs);
+    ok = ok && fe_is_zero_mod(t);
+    if (!ok) { atomicCAS(err, 0, i + 1); return; }
+    out[i].x = x; out[i].y = y;
+}
+// affine Montgomery -> reference layout (for rk_kzg_ctx_export_settings)
+__global__ void k_setup_to_ref(const G1Affine* in, int n, uint8_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp conv, x, y, one;
+    fe_const<FpTag, FP_TO_REF>(conv);
+    fe_mul(x, in[i].x, conv); fe_cond_sub_mod<FpTag>(x);
+    fe_mul(y, in[i].y, conv); fe_cond_sub_mod<FpTag>(y);
+    fe_const<FpTag, FP_ONE>(one);
+    fe_mul(one, one, conv); fe_cond_sub_mod<FpTag>(one);
+    uint32_t* w = reinterpret_cast<uint32_t*>(out + 144 * (size_t)i);
+    uint32_t t[12];
+    fe_pack<FpTag>(t, x);   for (int k = 0; k < 12; k++) w[k] = t[k];
+    fe_pack<FpTag>(t, y);   for (int k = 0; k < 12; k++) w[12 + k] = t[k];
+    fe_pack<FpTag>(t, one); for (int k = 0; k < 12; k++) w[24 + k] = t[k];
+}
+// 48-byte big-endian canonical Fp -> reference Montgomery limbs (G2 coordinates for export)
+__global__ void k_fp_be_to_ref(const uint8_t* in, int n, uint8_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[12];
+    for (int k = 0; k < 12; k++) w[k] = load_be32(in + 48 * (size_t)i + 4 * (11 - k));
+    Fp c, m, conv;
+    fe_unpack<FpTag>(c, w);
+    fe_to_mont(m, c);
+    fe_const<FpTag, FP_TO_REF>(conv);
+    fe_mul(m, m, conv); fe_cond_sub_mod<FpTag>(m);
+    fe_pack<FpTag>(w, m);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + 48 * (size_t)i);
+    for (int k = 0; k < 12; k++) o[k] = w[k];
+}
+// reference Montgomery limbs -> 48-byte big-endian canonical (G2 coordinates on import)
+__global__ void k_fp_ref_to_be(const uint8_t* in, int n, uint8_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* wi = reinterpret_cast<const uint32_t*>(in + 48 * (size_t)i);
+    uint32_t w[12];
+    for (int k = 0; k < 12; k++) w[k] = wi[k];
+    Fp v, conv, c;
+    fe_unpack<FpTag>(v, w);
+    fe_const<FpTag, FP_FROM_REF>(conv);
+    fe_mul(v, v, conv);
+    fe_from_mont(c, v);
+    fp_to_be48(out + 48 * (size_t)i, c);
+}
+
+// roots of unity.  kind 0: brp order w^brp(i), i < 4096 (ours, Montgomery 30-bit limbs).
+__global__ void k_roots_brp(Fr* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NPTS) return;
+    uint32_t e = __brev((uint32_t)i) >> 20;              // 12-bit reversal
+    Fr acc, base;
+    fe_const<FrTag, FR_ONE>(acc);
+    fe_const<FrTag, FR_OMEGA>(base);
+    for (int b = 0; b < 12; b++) {
+        if ((e >> b) & 1) fe_mul(acc, acc, base);
+        fe_sqr(base, base);
+    }
+    out[i] = acc;
+}
+// w^e(i) in the reference's Montgomery layout (R = 2^256, 4 x u64 LE) for export.
+// order 0: e = i (expanded, n = 4097); 1: e = 4096 - i (reverse); 2: e = brp(i).
+__global__ void k_roots_export(int order, int n, uint8_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t e = order == 0 ? (uint32_t)i : order == 1 ? (uint32_t)(4096 - i) : (__brev((uint32_t)i) >> 20);
+    Fr acc, base, conv;
+    fe_const<FrTag, FR_ONE>(acc);
+    fe_const<FrTag, FR_OMEGA>(base);
+    for (int b = 0; b < 13; b++) {
+        if ((e >> b) & 1) fe_mul(acc, acc, base);
+        fe_sqr(base, base);
+    }
+    fe_const<FrTag, FR_TO_REF>(conv);
+    fe_mul(acc, acc, conv); fe_cond_sub_mod<FrTag>(acc);
+    uint32_t w[8];
+    fe_pack<FrTag>(w, acc);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + 32 * (size_t)i);
+    for (int k = 0; k < 8; k++) o[k] = w[k];
+}
+
+// ---------------------------------------------------------------------------
+// Window-table construction
+// ---------------------------------------------------------------------------
+// Stage A: bases[i][j] = 2^(c j) * L_i in XYZZ (thread per point).
+__global__ void __launch_bounds__(64) k_table_bases(const G1Affine* g1, TableGeom g, G1Xyzz* bases) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NPTS) return;
+    G1Xyzz p;
+    g1_from_affine(p, g1[i]);
+    for (int j = 0; j < g.W; j++) {
+        bases[(size_t)i * g.W + j] = p;
+        if (j + 1 < g.W)
+            for (int k = 0; k < g.c; k++) { G1Xyzz t; g1_dbl(t, p); p = t; }
+    }
+}
+// Batch-normalise `count` consecutive XYZZ points per thread (Montgomery's trick, one
+// Fermat inversion per thread) and write them either as affine Montgomery points or
+// as packed table entries.  Points are never infinity here (multiples k*B, k < r).
+template <int G>
+__device__ __forceinline__ void normalize_run(const G1Xyzz* in, int count, G1Affine* out_aff, TableEntry* out_tab) {
+    Fp pre[G], run;
+    fe_const<FpTag, FP_ONE>(run);
+    for (int k = 0; k < count; k++) { pre[k] = run; fe_mul(run, run, in[k].zzz); }
+    Fp inv;
+    fe_inv(inv, run);
+    for (int k = count - 1; k >= 0; k--) {
+        G1Xyzz p = in[k];
+        Fp zi;
+        fe_mul(zi, inv, pre[k]);
+        fe_mul(inv, inv, p.zzz);
+        G1Affine a;
+        g1_to_affine_with_inv(a, p, zi);
+        if (out_aff) out_aff[k] = a;
+        if (out_tab) {
+            TableEntry e;
+            fe_pack<FpTag>(e.x, a.x);
+            fe_pack<FpTag>(e.y, a.y);
+            uint4* dst = reinterpret_cast<uint4*>(out_tab + k);
+            const uint4* src = reinterpret_cast<const uint4*>(&e);
+#pragma unroll
+            for (int q = 0; q < 6; q++) dst[q] = src[q];
+        }
+    }
+}
+__global__ void __launch_bounds__(64) k_table_bases_affine(const G1Xyzz* bases, int n, G1Affine* out) {
+    // thread per group of 16 consecutive bases
+    const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    const int start = grp * 16;
+    if (start >= n) return;
+    const int count = min(16, n - start);
+    normalize_run<16>(bases + start, count, out + start, nullptr);
+}
+// Stage B1: chain (i, j) advances D multiples: tmp[chain][k] = (d0 + k) * B_ij.
+// `state` carries the running multiple between launches.
+__global__ void __launch_bounds__(128) k_table_chain(const G1Affine* bases_aff, TableGeom g, uint32_t d0, int D,
+                                                     G1Xyzz* state, G1Xyzz* tmp) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= NPTS * g.W) return;
+    const int j = chain % g.W;
+    const uint32_t limit = (j == g.W - 1) ? g.top_entries : g.half;
+    if (d0 > limit) return;
+    G1Affine b = bases_aff[chain];
+    G1Xyzz acc;
+    if (d0 == 1) g1_set_inf(acc); else acc = state[chain];
+    G1Xyzz* o = tmp + (size_t)chain * D;
+    for (int k = 0; k < D; k++) {
+        if (d0 + k > limit) break;
+        g1_madd(acc, b.x, b.y);
+        o[k] = acc;
+    }
+    state[chain] = acc;
+}
+// Stage B2: normalise tmp into table entries; thread per (chain, group of G multiples).
+constexpr int TABLE_NORM_G = 32;
+__global__ void __launch_bounds__(128) k_table_normalize(TableGeom g, uint32_t d0, int D, const G1Xyzz* tmp,
+                                                         TableEntry* table) {
+    const int groups_per_chain = D / TABLE_NORM_G;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chain = (int)(gid / groups_per_chain);
+    const int grp = (int)(gid % groups_per_chain);
+    if (chain >= NPTS * g.W) return;
+    const int i = chain / g.W, j = chain % g.W;
+    const uint32_t limit = (j == g.W - 1) ? g.top_entries : g.half;
+    const uint32_t dstart = d0 + (uint32_t)grp * TABLE_NORM_G;
+    if (dstart > limit) return;
+    const int count = (int)min((uint32_t)TABLE_NORM_G, limit - dstart + 1);
+    TableEntry* dst = table + ((size_t)i * g.per_point + (size_t)j * g.half + (dstart - 1));
+    normalize_run<TABLE_NORM_G>(tmp + (size_t)chain * D + (size_t)grp * TABLE_NORM_G, count, nullptr, dst);
+}
+
+// ---------------------------------------------------------------------------
+// Integer-multiply peak (roofline denominator): independent mad.wide.u32 chains.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_imad_peak(uint64_t* out, uint32_t seed, int iters) {
+    uint64_t w[8];
+    uint32_t b = seed | 1u, c = threadIdx.x * 2654435761u + 12345u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(b), "r"(c));
+        }
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r ^= w[i];
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = r;
+}
+
+}  // namespace rk
