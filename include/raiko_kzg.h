@@ -45,7 +45,7 @@ typedef enum {
 /* ---- settings: replaces KZG_SETTINGS_BIN / KZG_SETTINGS (eip4844.rs:14-24) -------------
  * `settings` may be any of: kzg_settings_raw.bin (739 624 B), the bincode image
  * lib/kzg_settings/zkcrypto_kzg_settings.bin (1 001 905 B) that eip4844.rs:14 embeds, or
- * this repo's compact image ("RKZGTS01", compressed points).  `devices` lists CUDA device
+ * this repo's compact image ("RKZGTS02": compressed G1, affine G2).  `devices` lists CUDA device
  * ordinals (NULL/0 = current device only).  `window_bits` selects the fixed-base table
  * width c in 4..15 (0 = RAIKO_KZG_WINDOW_BITS from the environment, else the largest
  * table that fits comfortably in free HBM; c = 15 needs ~115 GB per GPU).              */
@@ -92,7 +92,9 @@ rk_status rk_calc_kzg_proof(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_le
  * ctx's devices, streamed in chunks, and the outputs are gathered at their blob index.
  * A blob that fails to deserialize sets per_blob_status[i] = RK_ERR_NONCANONICAL_FE and
  * leaves its outputs zeroed without failing the batch.  Any output pointer except the
- * first may be NULL.                                                                     */
+ * first may be NULL.  Device inputs must be complete on entry: work queued on the legacy
+ * default stream is ordered before the batch automatically, producers on other streams
+ * must be synchronised by the caller.  All outputs are complete when the call returns.   */
 rk_status rk_commit_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_t n,
                           uint8_t* out_commitments /* n*48 */,
                           uint8_t* out_versioned_hashes /* n*32 */,

@@ -312,10 +312,13 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
     }
     if (c < 4 || c > 15) return fail(RK_ERR_ARG, "window_bits %d outside 4..15", c);
     d->geom = make_geom(c);
-    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_main, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_sha, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+    // Blocking streams on purpose: they order after work already queued on the legacy default
+    // stream (where PyTorch produces device-resident blobs), so a device-pointer batch never
+    // reads a tensor that is still being written.  They do not serialise with each other.
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_main, cudaStreamDefault));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_sha, cudaStreamDefault));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_in, cudaStreamDefault));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->s_out, cudaStreamDefault));
     CUDA_TRY(cudaFuncSetAttribute(k_fr_eval_quot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM_BYTES));
     rk_status st = load_setup(d, settings, len, g2_be);
     if (st != RK_OK) return st;

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) {
                 else { idx = raw; carry = 0; }
             } else {
                 idx = s[0] + carry;
+                if (idx > prm.g.top_entries) idx = 0;     // only a scalar >= r gets here: blob is rejected anyway
             }
             if (idx != 0) {
                 const uint4* e = reinterpret_cast<const uint4*>(pbase + ((size_t)j * half + (idx - 1)));

@@ -1,0 +1,120 @@
+"""The product's limb arithmetic (raiko_b200/csrc/field30.cuh, g1.cuh), compiled for the host
+by tests/native/fieldcheck.cpp, against Python big integers.  Same headers the kernels use."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "native", "_build", "libfieldcheck.so")
+P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+@pytest.fixture(scope="module")
+def L():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO,
+                           os.path.join(HERE, "native", "fieldcheck.cpp")])
+    return ctypes.CDLL(SO)
+
+
+def limbs(v, n):
+    return (ctypes.c_uint32 * n)(*[(v >> (30 * i)) & ((1 << 30) - 1) for i in range(n)])
+
+
+def val(a, bits=30):
+    return sum(int(x) << (bits * i) for i, x in enumerate(a))
+
+
+@pytest.mark.parametrize("name,mod,n", [("fp", P, 13), ("fr", R, 9)])
+def test_montgomery_mul_sqr(L, name, mod, n):
+    rnd = random.Random(n)
+    MR = 1 << (30 * n)
+    mul, sqr = getattr(L, "fc_%s_mul" % name), getattr(L, "fc_%s_sqr" % name)
+    for t in range(6000):
+        if t < 4:
+            a = b = MR - 1                       # every limb 2^30-1: worst-case column sums
+        elif t < 2000:
+            a, b = rnd.randrange(8 * mod), rnd.randrange(8 * mod)
+        else:
+            a, b = rnd.randrange(min(MR, 25 * mod)), rnd.randrange(min(MR, 25 * mod))
+        out = (ctypes.c_uint32 * n)()
+        mul(limbs(a, n), limbs(b, n), out)
+        assert all(x < (1 << 30) for x in out[:n - 1])
+        r = val(out)
+        assert r % mod == a * b * pow(MR, -1, mod) % mod and r <= a * b // MR + mod
+        sqr(limbs(a, n), out)
+        r = val(out)
+        assert r % mod == a * a * pow(MR, -1, mod) % mod and r <= a * a // MR + mod
+
+
+def test_add_sub_zero_pack_inv(L):
+    rnd = random.Random(5)
+    for _ in range(3000):
+        a, b = rnd.randrange(8 * P), rnd.randrange(6 * P)
+        out = (ctypes.c_uint32 * 13)()
+        L.fc_fp_add(limbs(a, 13), limbs(b, 13), out)
+        assert val(out) == a + b
+        L.fc_fp_sub6(limbs(a, 13), limbs(b, 13), out)
+        assert val(out) == a - b + 6 * P
+    for k in range(9):
+        assert L.fc_fp_is_zero_mod(limbs(k * P, 13)) == 1
+        assert L.fc_fp_is_zero_mod(limbs(k * P + 1, 13)) == 0
+        assert L.fc_fp_is_zero_mod(limbs(k * P + (1 << 30), 13)) == 0
+    for _ in range(1000):
+        a = rnd.randrange(1 << 384)
+        w = (ctypes.c_uint32 * 12)()
+        L.fc_fp_pack(limbs(a, 13), w)
+        assert val(w, 32) == a
+        out = (ctypes.c_uint32 * 13)()
+        L.fc_fp_unpack(w, out)
+        assert val(out) == a
+        a = rnd.randrange(1 << 256)
+        w = (ctypes.c_uint32 * 8)()
+        L.fc_fr_pack(limbs(a, 9), w)
+        assert val(w, 32) == a
+        out = (ctypes.c_uint32 * 9)()
+        L.fc_fr_unpack(w, out)
+        assert val(out) == a
+    for _ in range(8):
+        a = rnd.randrange(1, P)
+        w = (ctypes.c_uint32 * 12)(*[(a >> (32 * i)) & 0xFFFFFFFF for i in range(12)])
+        out = (ctypes.c_uint32 * 12)()
+        L.fc_fp_inv(w, out)
+        assert val(out, 32) == pow(a, -1, P)
+        a = rnd.randrange(1, R)
+        w = (ctypes.c_uint32 * 8)(*[(a >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+        out = (ctypes.c_uint32 * 8)()
+        L.fc_fr_inv(w, out)
+        assert val(out, 32) == pow(a, -1, R)
+
+
+def test_g1_formulas_and_exceptional_cases(L, pyoracle):
+    o, s = pyoracle
+    rnd = random.Random(9)
+    INF = o.g1_compress(None)
+    buf = lambda: ctypes.create_string_buffer(48)  # noqa: E731
+    pts = [o.g1_mul(o.G1_GEN, rnd.randrange(1, R)) for _ in range(6)]
+    for pt in pts + [None]:
+        out = buf()
+        assert L.fc_g1_roundtrip(o.g1_compress(pt), out) == 0 and out.raw == o.g1_compress(pt)
+    for i, a in enumerate(pts):
+        b = pts[(i + 1) % len(pts)]
+        ca, cb = o.g1_compress(a), o.g1_compress(b)
+        for fn in (L.fc_g1_add, L.fc_g1_madd):
+            out = buf(); fn(ca, cb, out); assert out.raw == o.g1_compress(o.g1_add(a, b))          # generic
+            out = buf(); fn(ca, ca, out); assert out.raw == o.g1_compress(o.g1_add(a, a))          # P + P
+            out = buf(); fn(ca, o.g1_compress(o.g1_neg(a)), out); assert out.raw == INF            # P + (-P)
+            out = buf(); fn(INF, ca, out); assert out.raw == ca                                    # O + P
+        out = buf(); L.fc_g1_add(ca, INF, out); assert out.raw == ca
+        out = buf(); L.fc_g1_dbl(ca, out); assert out.raw == o.g1_compress(o.g1_add(a, a))
+        k = rnd.randrange(1 << 64)
+        out = buf(); L.fc_g1_mul_u64(ca, ctypes.c_uint64(k), out); assert out.raw == o.g1_compress(o.g1_mul(a, k))
+    out = buf(); L.fc_g1_dbl(INF, out); assert out.raw == INF
+    # 4096 decompressions + a 4095-addition chain: sum of the Lagrange setup = generator
+    allpts = b"".join(o.g1_compress(p) for p in s.g1)
+    out = buf()
+    assert L.fc_g1_sum(allpts, 4096, out) == 0 and out.raw == o.g1_compress(o.G1_GEN)

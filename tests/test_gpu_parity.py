@@ -1,0 +1,256 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle and the
+committed golden fixtures.  Bit-exact (integer / byte work).  Run with -m gpu on a B200."""
+import ctypes
+import os
+import random
+import subprocess
+import sys
+
+import pytest
+
+from kzg_testlib import ROOT, blob_from_recipe, synthetic_blob
+
+pytestmark = pytest.mark.gpu
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+def rand_blob(rnd, nonzero_fraction=1.0):
+    out = bytearray()
+    for _ in range(4096):
+        v = rnd.randrange(R) if rnd.random() < nonzero_fraction else 0
+        out += v.to_bytes(32, "big")
+    return bytes(out)
+
+
+def test_golden_vectors_batch_api(gpu_settings, golden):
+    import raiko_b200 as rk
+    cases = golden["cases"]
+    blobs = [blob_from_recipe(c["recipe"]) for c in cases]
+    res = rk.commit_prove_batch(blobs, gpu_settings)
+    for i, c in enumerate(cases):
+        p0 = c["proofs"][0]
+        got = (res.commitments[i].hex(), res.versioned_hashes[i].hex(), res.xs[i].hex(), res.ys[i].hex(), res.proofs[i].hex())
+        assert got == (c["commitment"], c["versioned_hash"], p0["z"], p0["y"], p0["proof"]), c["name"]
+        assert res.status[i] == 0
+    res = rk.commit_batch(blobs, gpu_settings)
+    assert [x.hex() for x in res.commitments] == [c["commitment"] for c in cases]
+    assert [x.hex() for x in res.versioned_hashes] == [c["versioned_hash"] for c in cases]
+
+
+def test_golden_vectors_single_call_api(gpu_settings, golden):
+    """The reference's own function names, one blob per call (eip4844.rs:44-99)."""
+    import raiko_b200 as rk
+    for c in golden["cases"]:
+        blob = blob_from_recipe(c["recipe"])
+        p0 = c["proofs"][0]
+        commitment = rk.calc_kzg_proof_commitment(blob, gpu_settings)
+        assert commitment.hex() == c["commitment"]
+        assert rk.blob_to_kzg_commitment(blob, gpu_settings) == commitment
+        vh = rk.commitment_to_version_hash(commitment)
+        assert vh.hex() == c["versioned_hash"]
+        assert rk.get_evaluation_point(blob, vh, gpu_settings).hex() == p0["z"]
+        assert tuple(v.hex() for v in rk.proof_of_equivalence(blob, vh, gpu_settings)) == (p0["z"], p0["y"])
+        assert rk.calc_kzg_proof(blob, vh, gpu_settings).hex() == p0["proof"]
+        for p in c["proofs"]:
+            z = bytes.fromhex(p["z"])
+            proof, y = rk.compute_kzg_proof(blob, z, gpu_settings)
+            assert (proof.hex(), y.hex()) == (p["proof"], p["y"]), (c["name"], p["label"])
+            assert rk.kzg_proof_to_bytes(rk.calc_kzg_proof_with_point(blob, z, gpu_settings)).hex() == p["proof"]
+
+
+def test_reference_kat_and_structural_anchor(gpu_settings):
+    import raiko_b200 as rk
+    c = rk.calc_kzg_proof_commitment(bytes(131072), gpu_settings)       # eip4844.rs:147-160
+    assert "0x" + rk.commitment_to_version_hash(c).hex() == "0x010657f37554c781402a22917dee2f75def7ab966d7b770905398eba3c444014"
+    ones = rk.calc_kzg_proof_commitment((1).to_bytes(32, "big") * 4096, gpu_settings)
+    assert ones.hex().startswith("97f1d3a73197d794")                      # G1 generator
+
+
+def test_deserialize_errors(gpu_settings, golden):
+    import raiko_b200 as rk
+    for e in golden["errors"]:
+        blob = blob_from_recipe(e["recipe"])
+        with pytest.raises(rk.DeserializeBlob):
+            rk.calc_kzg_proof_commitment(blob, gpu_settings)
+        with pytest.raises(rk.DeserializeBlob):
+            rk.proof_of_equivalence(blob, bytes(32), gpu_settings)
+        with pytest.raises(rk.DeserializeBlob):
+            rk.calc_kzg_proof(blob, bytes(32), gpu_settings)
+    for bad_len in (0, 32, 131071, 131073):
+        with pytest.raises(rk.DeserializeBlob):
+            rk.calc_kzg_proof_commitment(bytes(bad_len), gpu_settings)
+
+
+def test_bad_blob_inside_batch_does_not_fail_the_batch(gpu_settings, golden, ref):
+    import raiko_b200 as rk
+    good = [synthetic_blob(b, seed=5) for b in range(3)]
+    bad = blob_from_recipe(golden["errors"][1]["recipe"])
+    blobs = [good[0], bad, good[1], bad, good[2]]
+    res = rk.commit_prove_batch(blobs, gpu_settings)
+    assert res.status == [0, 2, 0, 2, 0]
+    for i in (1, 3):
+        assert res.commitments[i] == bytes(48) and res.proofs[i] == bytes(48)
+        assert res.xs[i] == bytes(32) and res.ys[i] == bytes(32) and res.versioned_hashes[i] == bytes(32)
+    for i, g in zip((0, 2, 4), good):
+        assert (res.commitments[i], res.versioned_hashes[i], res.xs[i], res.ys[i], res.proofs[i]) == ref.commit_prove(g)
+
+
+def test_random_blobs_against_c_oracle(gpu_settings, ref):
+    import raiko_b200 as rk
+    rnd = random.Random(20241018)
+    blobs = [rand_blob(rnd) for _ in range(6)] + [rand_blob(rnd, 0.01), rand_blob(rnd, 0.5)]
+    # short scalars and extreme digits: every window digit at its maximum / carry boundary
+    edge_vals = [R - 1, R - 2, 1, 2, (1 << 254) - 1, 1 << 254, (1 << 255) - 19 - (1 << 254), 0x7FFF, 0x8000, 0x4000, 0x3FFF,
+                 int("7f" * 31, 16), int("80" * 31, 16) % R, int("ff" * 31, 16), (1 << 240) - 1, 1 << 240]
+    blobs.append(b"".join(edge_vals[i % len(edge_vals)].to_bytes(32, "big") for i in range(4096)))
+    res = rk.commit_prove_batch(blobs, gpu_settings)
+    for i, blob in enumerate(blobs):
+        assert (res.commitments[i], res.versioned_hashes[i], res.xs[i], res.ys[i], res.proofs[i]) == ref.commit_prove(blob), i
+    zs = [rnd.randrange(1 << 256).to_bytes(32, "big") for _ in blobs]           # z >= r is reduced, not rejected
+    res2 = rk.compute_kzg_proof_batch(blobs, zs, gpu_settings)
+    for i, blob in enumerate(blobs):
+        assert (res2.proofs[i], res2.ys[i]) == ref.compute_proof(blob, zs[i]), i
+
+
+def test_chunked_pipeline_and_device_pointers(golden, ref):
+    """n > chunk exercises slot reuse; torch CUDA tensors exercise the device-pointer path."""
+    code = r'''
+import os, sys, ctypes
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests")); sys.path.insert(0, os.path.join(%r, "oracle"))
+import torch
+import raiko_b200 as rk
+from raiko_b200 import _native
+import kzg_ref
+from kzg_testlib import SETUP, synthetic_blob
+s = rk.KzgSettings(window_bits=8)
+ref = kzg_ref.RefSettings(open(SETUP, "rb").read())
+n = 21
+blobs = [synthetic_blob(b, seed=99) for b in range(n)]
+host = rk.commit_prove_batch(blobs, s)
+t = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).cuda()
+lib = _native.load()
+outs = {k: torch.zeros((n, w), dtype=torch.uint8, device="cuda") for k, w in (("c", 48), ("vh", 32), ("x", 32), ("y", 32), ("p", 48), ("st", 1))}
+st = lib.rk_commit_prove_batch(s._ctx, t.data_ptr(), n, outs["c"].data_ptr(), outs["vh"].data_ptr(), outs["x"].data_ptr(), outs["y"].data_ptr(), outs["p"].data_ptr(), outs["st"].data_ptr())
+assert st == 0, _native.last_error()
+torch.cuda.synchronize()
+for i in range(n):
+    want = ref.commit_prove(blobs[i]) if i %% 5 == 0 else None
+    got = (host.commitments[i], host.versioned_hashes[i], host.xs[i], host.ys[i], host.proofs[i])
+    dev = tuple(outs[k][i].cpu().numpy().tobytes() for k in ("c", "vh", "x", "y", "p"))
+    assert got == dev, i
+    if want: assert got == want, i
+assert int(outs["st"].sum()) == 0
+print("CHUNK_OK", s.stats()["total_launches"])
+''' % (ROOT, ROOT, ROOT)
+    env = dict(os.environ, RAIKO_KZG_CHUNK="4")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "CHUNK_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_linearity_and_pairing_on_a_larger_batch(gpu_settings, pyoracle, ref):
+    """Size-independent properties: commit is linear in the blob, and sampled
+    (C, x, y, proof) tuples satisfy the pairing equation the reference tests (eip4844.rs:176-183)."""
+    import raiko_b200 as rk
+    o, s = pyoracle
+    rnd = random.Random(7)
+    n = 48
+    blobs = [synthetic_blob(b, seed=31337) for b in range(n)]
+    sums = [0] * 4096
+    for blob in blobs:
+        for i in range(4096):
+            sums[i] += int.from_bytes(blob[32 * i:32 * i + 32], "big")
+    sum_blob = b"".join((v % R).to_bytes(32, "big") for v in sums)
+    res = rk.commit_prove_batch(blobs + [sum_blob], gpu_settings)
+    acc = None
+    for c in res.commitments[:n]:
+        acc = o.g1_add(acc, o.g1_decompress(c))
+    assert o.g1_compress(acc) == res.commitments[n]
+    for i in rnd.sample(range(n), 2):
+        assert o.verify_kzg_proof(res.commitments[i], int.from_bytes(res.xs[i], "big"), int.from_bytes(res.ys[i], "big"), res.proofs[i], s)
+    i = rnd.randrange(n)
+    assert (res.commitments[i], res.versioned_hashes[i], res.xs[i], res.ys[i], res.proofs[i]) == ref.commit_prove(blobs[i])
+
+
+def test_settings_images_and_export(gpu_settings, setup_bytes):
+    """Row a1: every on-disk form loads to the same table, and re-serialising reproduces the
+    reference's files byte for byte (sha256 from SURVEY.md Appendix A)."""
+    import hashlib
+    import raiko_b200 as rk
+    raw = gpu_settings.export("raw")
+    bc = gpu_settings.export("bincode")
+    assert len(raw) == 739624 and hashlib.sha256(raw).hexdigest() == "b2fef63491219899427a1cf4fe09380cbc7d85e5969e105c13279056eac38092"
+    assert len(bc) == 1001905 and hashlib.sha256(bc).hexdigest() == "1b4de2ed5ebaae9ff855851ece64012dc5b334f8a128f713f5dec8f88b472359"
+    blob = synthetic_blob(1)
+    want = rk.calc_kzg_proof_commitment(blob, gpu_settings)
+    for img in (raw, bc):
+        s2 = rk.KzgSettings(img, window_bits=6)
+        assert rk.calc_kzg_proof_commitment(blob, s2) == want
+        s2.close()
+    with pytest.raises(ValueError):
+        rk.KzgSettings(setup_bytes[:-1])
+    corrupted = bytearray(setup_bytes)
+    corrupted[16 + 48 * 100 + 20] ^= 1
+    with pytest.raises(ValueError):
+        rk.KzgSettings(bytes(corrupted), window_bits=6)
+
+
+@pytest.mark.parametrize("wb", [4, 11, 15])
+def test_other_window_widths(wb, golden):
+    import torch
+    import raiko_b200 as rk
+    if wb == 15 and torch.cuda.mem_get_info()[0] < 130e9:
+        pytest.skip("not enough free HBM for the c=15 table")
+    s = rk.KzgSettings(window_bits=wb)
+    assert s.window_bits == wb
+    cases = [c for c in golden["cases"] if c["name"] in ("C1_zero", "C3_mod64", "C5_syn0", "M1_max", "C6_syn1")]
+    res = rk.commit_prove_batch([blob_from_recipe(c["recipe"]) for c in cases], s)
+    for i, c in enumerate(cases):
+        assert (res.commitments[i].hex(), res.proofs[i].hex(), res.ys[i].hex()) == (c["commitment"], c["proofs"][0]["proof"], c["proofs"][0]["y"])
+    s.close()
+
+
+def test_thread_safety(gpu_settings, golden):
+    """Up to 16 requests are in flight in the reference (host/src/proof.rs:121)."""
+    import threading
+    import raiko_b200 as rk
+    cases = golden["cases"][:8]
+    blobs = [blob_from_recipe(c["recipe"]) for c in cases]
+    errs = []
+
+    def work(k):
+        try:
+            for rep in range(2):
+                i = (k + rep) % len(cases)
+                assert rk.calc_kzg_proof_commitment(blobs[i], gpu_settings).hex() == cases[i]["commitment"]
+                vh = bytes.fromhex(cases[i]["versioned_hash"])
+                assert rk.calc_kzg_proof(blobs[i], vh, gpu_settings).hex() == cases[i]["proofs"][0]["proof"]
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(16)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+
+
+def test_multi_gpu_sharding(golden, ref):
+    import torch
+    import raiko_b200 as rk
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    s = rk.KzgSettings(devices=list(range(min(4, torch.cuda.device_count()))), window_bits=8)
+    blobs = [synthetic_blob(b, seed=4242) for b in range(11)]
+    res = rk.commit_prove_batch(blobs, s)
+    for i in (0, 3, 5, 10):
+        assert (res.commitments[i], res.versioned_hashes[i], res.xs[i], res.ys[i], res.proofs[i]) == ref.commit_prove(blobs[i])
+    one = rk.KzgSettings(devices=[0], window_bits=8)
+    res1 = rk.commit_prove_batch(blobs, one)
+    assert res1.commitments == res.commitments and res1.proofs == res.proofs and res1.ys == res.ys
+    s.close(); one.close()
+
+
+def test_imad_peak_microbenchmark():
+    from raiko_b200 import _native
+    lib = _native.load()
+    peak, clk = ctypes.c_double(), ctypes.c_double()
+    assert lib.rk_measure_imad_peak(0, ctypes.byref(peak), ctypes.byref(clk)) == 0
+    assert 5e12 < peak.value < 40e12
