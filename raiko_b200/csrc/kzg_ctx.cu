@@ -101,6 +101,8 @@ struct DeviceCtx {
     uint8_t* d_status = nullptr;           // chunk (status bytes), part of d_out really
     std::mutex mu;
     int sm_count = 148;
+    int msm_variant = 255;                 // register budget of the MSM kernel (RAIKO_KZG_MSM_REGS)
+    int warps_per_sm = 8;
     // stats
     bool stats_on = false;
     std::vector<KernelTimer> timers;
@@ -295,6 +297,8 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, d->dev));
     d->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("RAIKO_KZG_MSM_REGS")) d->msm_variant = atoi(e);
+    d->warps_per_sm = d->msm_variant == 128 ? 16 : d->msm_variant == 168 ? 12 : 8;
     if (prop.major < 10)
         return fail(RK_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", d->dev, prop.major, prop.minor);
     int c = window_bits;
@@ -348,7 +352,7 @@ struct BatchArgs {
 
 int pick_splits_log2(const DeviceCtx* d, size_t nblobs) {
     // enough warps to fill the machine (8 resident warps per SM), at most 32 per blob
-    const size_t target = (size_t)d->sm_count * 8;
+    const size_t target = (size_t)d->sm_count * d->warps_per_sm;
     int lg = 0;
     while (lg < 5 && (nblobs << lg) < target) lg++;
     return lg;
@@ -360,9 +364,10 @@ void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint3
     p.splits_log2 = pick_splits_log2(d, (size_t)n);
     p.partials = s.d_partials; p.bad = bad;
     const long long warps = (long long)n << p.splits_log2;
-    const unsigned blocks = (unsigned)((warps + 7) / 8);
     timer_begin(d, d->s_main, T_MSM);
-    k_msm<<<blocks, 256, 0, d->s_main>>>(p);
+    if (d->msm_variant == 168) k_msm_r168<<<(unsigned)((warps + 11) / 12), 384, 0, d->s_main>>>(p);
+    else if (d->msm_variant == 128) k_msm_r128<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
+    else k_msm<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
     timer_end(d, d->s_main);
     d->stats.msm_point_adds += (uint64_t)n * NPTS * d->geom.W;
     *splits_out = 1 << p.splits_log2;

@@ -84,7 +84,8 @@ __device__ __forceinline__ void load_scalar_be(uint32_t (&s)[8], const uint8_t* 
     s[1] = __byte_perm(lo.z, 0, 0x0123); s[0] = __byte_perm(lo.w, 0, 0x0123);
 }
 
-__global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) {
+template <int THREADS, int MIN_BLOCKS>
+__device__ __forceinline__ void msm_body(const MsmParams& prm) {
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int blob = warp >> prm.splits_log2;
@@ -167,6 +168,13 @@ __global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) {
     }
     if (lane == 0) prm.partials[warp] = acc;
 }
+
+
+// Register-budget variants of the same body (occupancy vs. spills is an empirical trade):
+//   255 regs x 8 warps/SM, 168 regs x 12 warps/SM, 128 regs x 16 warps/SM.
+__global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) { msm_body<256, 1>(prm); }
+__global__ void __launch_bounds__(384, 1) k_msm_r168(MsmParams prm) { msm_body<384, 1>(prm); }
+__global__ void __launch_bounds__(256, 2) k_msm_r128(MsmParams prm) { msm_body<256, 2>(prm); }
 
 // ---------------------------------------------------------------------------
 // k_finalize: one thread per blob.  Sums the blob's partial sums, converts to affine
