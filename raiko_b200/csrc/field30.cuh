@@ -81,8 +81,26 @@ struct Fe {
     uint32_t v[F::N];
 };
 
-// c += a * b  (32 x 32 + 64 -> 64, no carry out): one IMAD.WIDE.U32.
-RK_HD void mac(uint64_t& c, uint32_t a, uint32_t b) { c += (uint64_t)a * b; }
+// c += a * b  (32 x 32 + 64 -> 64, no carry out).
+// RK_MAC_FORM selects how the device code states it (measured, profiles/r01/):
+//   0: C expression  -> ptxas fuses to IMAD.WIDE.U32 Rd, Ra, Rb, Rc.  With two register
+//      multiplicands AND a 64-bit register addend this form issues at HALF rate on B200
+//      (4 source words; 29/clk/SM vs 60/clk/SM for the immediate or RZ-addend forms).
+//   1: PTX mad.wide.u32 -> ptxas splits it into IMAD.WIDE.U32 Rd, Ra, Rb, RZ (full rate)
+//      plus 3-input 64-bit IADD3 / IADD3.X adds on the ALU pipe.
+#ifndef RK_MAC_FORM
+#define RK_MAC_FORM 0
+#endif
+RK_HD void mac(uint64_t& c, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__) && RK_MAC_FORM == 1
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c) : "r"(a), "r"(b));
+#else
+    c += (uint64_t)a * b;
+#endif
+}
+// same with a compile-time constant multiplicand (Montgomery reduction rows): the
+// immediate form of IMAD.WIDE keeps its 64-bit addend at full rate.
+RK_HD void mac_const(uint64_t& c, uint32_t a, uint32_t k) { c += (uint64_t)a * k; }
 
 // Hide a 32-bit value's provenance from the optimiser (emits no instruction).
 // Without this, LLVM sees `(uint64_t)(x & 0x3fffffff) * y`, rewrites the operand
@@ -123,7 +141,7 @@ RK_HD void mont_reduce_columns(Fe<F>& r, uint64_t (&c)[2 * F::N]) {
     for (int i = 0; i < N; i++) {
         uint32_t m = launder(((uint32_t)c[i] * F::PINV) & LIMB_MASK);
 #pragma unroll
-        for (int j = 0; j < N; j++) mac(c[i + j], m, F::MOD::at(j));
+        for (int j = 0; j < N; j++) mac_const(c[i + j], m, F::MOD::at(j));
         c[i + 1] += c[i] >> LIMB_BITS;   // low 30 bits of c[i] are zero now
     }
     // result = columns N .. 2N-1, normalised

@@ -84,12 +84,16 @@ __device__ __forceinline__ void load_scalar_be(uint32_t (&s)[8], const uint8_t* 
     s[1] = __byte_perm(lo.z, 0, 0x0123); s[0] = __byte_perm(lo.w, 0, 0x0123);
 }
 
-template <int THREADS, int MIN_BLOCKS>
+template <int THREADS, int MIN_BLOCKS, int SYNC_EVERY>
 __device__ __forceinline__ void msm_body(const MsmParams& prm) {
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    const int blob = warp >> prm.splits_log2;
-    if (blob >= prm.nblobs) return;
+    const int blob_raw = warp >> prm.splits_log2;
+    // Warps past the end of the batch (only in the last CTA) redo the last blob and drop the
+    // result: every warp of a CTA must reach the barriers below, and a predicate around the
+    // hot loop costs registers.
+    const bool live = blob_raw < prm.nblobs;
+    const int blob = live ? blob_raw : prm.nblobs - 1;
     const int split = warp & ((1 << prm.splits_log2) - 1);
     const int pts_per_warp = NPTS >> prm.splits_log2;
     const int per_lane = pts_per_warp >> 5;
@@ -113,6 +117,10 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
     for (int it = 0; it <= total; it++) {
         uint4 nxt[6];
         int nxt_kind = 0;
+        // Keep the CTA's warps in step: the addition below is ~85 KB of straight-line code, far
+        // more than the instruction cache holds, so warps that drift apart each stream it from
+        // L2 separately.  In step, one fetch serves all of them.
+        if (SYNC_EVERY > 0 && (it % SYNC_EVERY) == 0) __syncthreads();
         if (it < total) {
             if (j == 0) {
                 const int pt = first_pt + 32 * t;
@@ -157,7 +165,7 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
         cur_kind = nxt_kind;
     }
 
-    if (prm.bad != nullptr && __any_sync(0xffffffffu, any_bad) && lane == 0) atomicOr(prm.bad + blob, 1u);
+    if (live && prm.bad != nullptr && __any_sync(0xffffffffu, any_bad) && lane == 0) atomicOr(prm.bad + blob, 1u);
 
     // combine the 32 lane sums
     for (int delta = 16; delta >= 1; delta >>= 1) {
@@ -166,15 +174,16 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
         shfl_fp(o.zz, acc.zz, delta); shfl_fp(o.zzz, acc.zzz, delta);
         if (lane < delta) g1_add(acc, o);
     }
-    if (lane == 0) prm.partials[warp] = acc;
+    if (live && lane == 0) prm.partials[warp] = acc;
 }
 
 
 // Register-budget variants of the same body (occupancy vs. spills is an empirical trade):
 //   255 regs x 8 warps/SM, 168 regs x 12 warps/SM, 128 regs x 16 warps/SM.
-__global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) { msm_body<256, 1>(prm); }
-__global__ void __launch_bounds__(384, 1) k_msm_r168(MsmParams prm) { msm_body<384, 1>(prm); }
-__global__ void __launch_bounds__(256, 2) k_msm_r128(MsmParams prm) { msm_body<256, 2>(prm); }
+__global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) { msm_body<256, 1, 1>(prm); }
+__global__ void __launch_bounds__(256, 1) k_msm_nosync(MsmParams prm) { msm_body<256, 1, 0>(prm); }
+__global__ void __launch_bounds__(384, 1) k_msm_r168(MsmParams prm) { msm_body<384, 1, 1>(prm); }
+__global__ void __launch_bounds__(256, 2) k_msm_r128(MsmParams prm) { msm_body<256, 2, 1>(prm); }
 
 // ---------------------------------------------------------------------------
 // k_finalize: one thread per blob.  Sums the blob's partial sums, converts to affine
