@@ -60,7 +60,31 @@ RK_HD void g1_dbl(G1Xyzz& r, const G1Xyzz& a) {
     fe_set(r.x, X3);
 }
 
+// Out-of-line Fp product / square for the MSM hot loop.  Inlined, one mixed addition is ~85 KB
+// of straight-line code (10 products), far beyond the instruction cache; called, the loop body
+// is ~15 KB.  The CUDA ABI keeps both 13-word operands and the result in registers (checked:
+// no local-memory traffic, tools/ubench/noinline_test.cu), and the call costs ~3 %.
+#ifdef __CUDACC__
+__device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) { Fp r; fe_mul(r, a, b); return r; }
+__device__ __noinline__ Fp fp_sqr_call(Fp a) { Fp r; fe_sqr(r, a); return r; }
+#endif
+template <bool CALLS>
+RK_HD void fp_mul_sel(Fp& r, const Fp& a, const Fp& b) {
+#ifdef __CUDA_ARCH__
+    if (CALLS) { r = fp_mul_call(a, b); return; }
+#endif
+    fe_mul(r, a, b);
+}
+template <bool CALLS>
+RK_HD void fp_sqr_sel(Fp& r, const Fp& a) {
+#ifdef __CUDA_ARCH__
+    if (CALLS) { r = fp_sqr_call(a); return; }
+#endif
+    fe_sqr(r, a);
+}
+
 // acc += (x2, y2) affine (never infinity).
+template <bool CALLS = false>
 RK_HD void g1_madd(G1Xyzz& acc, const Fp& x2, const Fp& y2) {
     if (g1_is_inf(acc)) {
         fe_set(acc.x, x2); fe_set(acc.y, y2);
@@ -68,8 +92,8 @@ RK_HD void g1_madd(G1Xyzz& acc, const Fp& x2, const Fp& y2) {
         return;
     }
     Fp P, Rr, PP, PPP, Q, t;
-    fe_mul(P, x2, acc.zz);
-    fe_mul(Rr, y2, acc.zzz);
+    fp_mul_sel<CALLS>(P, x2, acc.zz);
+    fp_mul_sel<CALLS>(Rr, y2, acc.zzz);
     fe_sub<FpTag, 6>(P, P, acc.x);          // < 7.1p
     fe_sub<FpTag, 6>(Rr, Rr, acc.y);
     if (fe_is_zero_mod(P)) {
@@ -83,19 +107,19 @@ RK_HD void g1_madd(G1Xyzz& acc, const Fp& x2, const Fp& y2) {
         }
         return;
     }
-    fe_sqr(PP, P);
-    fe_mul(PPP, P, PP);
-    fe_mul(Q, acc.x, PP);
-    fe_sqr(acc.x, Rr);                      // X3 = R^2 - PPP - 2Q
+    fp_sqr_sel<CALLS>(PP, P);
+    fp_mul_sel<CALLS>(PPP, P, PP);
+    fp_mul_sel<CALLS>(Q, acc.x, PP);
+    fp_sqr_sel<CALLS>(acc.x, Rr);           // X3 = R^2 - PPP - 2Q
     fe_add(t, Q, Q);
     fe_add(t, t, PPP);                      // < 3.1p
     fe_sub<FpTag, 4>(acc.x, acc.x, t);      // < 5.1p
     fe_sub<FpTag, 6>(t, Q, acc.x);          // < 7.1p
-    fe_mul(t, Rr, t);
-    fe_mul(Q, acc.y, PPP);
+    fp_mul_sel<CALLS>(t, Rr, t);
+    fp_mul_sel<CALLS>(Q, acc.y, PPP);
     fe_sub<FpTag, 2>(acc.y, t, Q);          // < 3.1p
-    fe_mul(acc.zz, acc.zz, PP);
-    fe_mul(acc.zzz, acc.zzz, PPP);
+    fp_mul_sel<CALLS>(acc.zz, acc.zz, PP);
+    fp_mul_sel<CALLS>(acc.zzz, acc.zzz, PPP);
 }
 
 // a += b (both XYZZ)

@@ -367,6 +367,7 @@ void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint3
     timer_begin(d, d->s_main, T_MSM);
     if (d->msm_variant == 168) k_msm_r168<<<(unsigned)((warps + 11) / 12), 384, 0, d->s_main>>>(p);
     else if (d->msm_variant == 128) k_msm_r128<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
+    else if (d->msm_variant == 253) k_msm_calls<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
     else if (d->msm_variant == 254) k_msm_nosync<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
     else k_msm<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
     timer_end(d, d->s_main);

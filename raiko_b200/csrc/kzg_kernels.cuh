@@ -84,7 +84,7 @@ __device__ __forceinline__ void load_scalar_be(uint32_t (&s)[8], const uint8_t* 
     s[1] = __byte_perm(lo.z, 0, 0x0123); s[0] = __byte_perm(lo.w, 0, 0x0123);
 }
 
-template <int THREADS, int MIN_BLOCKS, int SYNC_EVERY>
+template <int THREADS, int MIN_BLOCKS, int SYNC_EVERY, bool CALLS>
 __device__ __forceinline__ void msm_body(const MsmParams& prm) {
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -158,7 +158,7 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
             fe_unpack<FpTag>(x2, w);
             fe_unpack<FpTag>(y2, w + 12);
             if (cur_kind == 2) fe_neg<FpTag, 2>(y2, y2);
-            g1_madd(acc, x2, y2);
+            g1_madd<CALLS>(acc, x2, y2);
         }
 #pragma unroll
         for (int k = 0; k < 6; k++) cur[k] = nxt[k];
@@ -180,10 +180,11 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
 
 // Register-budget variants of the same body (occupancy vs. spills is an empirical trade):
 //   255 regs x 8 warps/SM, 168 regs x 12 warps/SM, 128 regs x 16 warps/SM.
-__global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) { msm_body<256, 1, 1>(prm); }
-__global__ void __launch_bounds__(256, 1) k_msm_nosync(MsmParams prm) { msm_body<256, 1, 0>(prm); }
-__global__ void __launch_bounds__(384, 1) k_msm_r168(MsmParams prm) { msm_body<384, 1, 1>(prm); }
-__global__ void __launch_bounds__(256, 2) k_msm_r128(MsmParams prm) { msm_body<256, 2, 1>(prm); }
+__global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) { msm_body<256, 1, 1, false>(prm); }
+__global__ void __launch_bounds__(256, 1) k_msm_calls(MsmParams prm) { msm_body<256, 1, 0, true>(prm); }
+__global__ void __launch_bounds__(256, 1) k_msm_nosync(MsmParams prm) { msm_body<256, 1, 0, false>(prm); }
+__global__ void __launch_bounds__(384, 1) k_msm_r168(MsmParams prm) { msm_body<384, 1, 0, true>(prm); }
+__global__ void __launch_bounds__(256, 2) k_msm_r128(MsmParams prm) { msm_body<256, 2, 0, true>(prm); }
 
 // ---------------------------------------------------------------------------
 // k_finalize: one thread per blob.  Sums the blob's partial sums, converts to affine
