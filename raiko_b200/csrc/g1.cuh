@@ -169,6 +169,28 @@ RK_HD void g1_to_affine_with_inv(G1Affine& r, const G1Xyzz& a, const Fp& zzz_inv
     fe_mul(r.y, a.y, zzz_inv);
 }
 
+// r = k * p, k given as 8 little-endian 32-bit words (plain double-and-add; variable-base
+// work is off the throughput path: verification and tests only).
+RK_HD_NOINLINE void g1_scalar_mul(G1Xyzz& r, const G1Affine& p, const uint32_t* k) {
+    G1Xyzz acc;
+    g1_set_inf(acc);
+    for (int bit = 255; bit >= 0; bit--) {
+        G1Xyzz t;
+        g1_dbl(t, acc);
+        acc = t;
+        if ((k[bit >> 5] >> (bit & 31)) & 1) g1_madd(acc, p.x, p.y);
+    }
+    r = acc;
+}
+// XYZZ -> affine (one Fermat inversion).  Returns false for infinity.
+RK_HD bool g1_xyzz_to_affine(G1Affine& r, const G1Xyzz& a) {
+    if (g1_is_inf(a)) return false;
+    Fp inv;
+    fe_inv(inv, a.zzz);
+    g1_to_affine_with_inv(r, a, inv);
+    return true;
+}
+
 // ---------------------------------------------------------------------------
 // Serialisation (reference ZG1::to_bytes via
 // kzg_proof_to_bytes, lib/src/primitives/eip4844.rs:97-99)

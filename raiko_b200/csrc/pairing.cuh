@@ -1,0 +1,335 @@
+// BLS12-381 pairing product check (device + host), for verify_kzg_proof /
+// verify_blob_kzg_proof_batch (the equation the
+// reference tests at lib/src/primitives/eip4844.rs:176-183).
+//
+// Deliberately simple and obviously correct rather than fast -- two pairings close a whole
+// batch, so this is not on the throughput path:
+//   * Fq  : Fp kept strictly below 2p ("strict" wrappers over field30.cuh)
+//   * Fp2 = Fq[i]/(i^2 + 1)
+//   * Fp12 = Fq[w]/(w^12 - 2 w^6 + 2)  (i = w^6 - 1); schoolbook products
+//   * G2 on the twist y^2 = x^3 + 4(1 + i), affine; lines scaled by w^3 (killed by the
+//     final exponentiation because w^3 lies in Fp4)
+//   * Miller loop over |x| = 0xd201000000010000, shared squarings for all pairs
+//   * final exponentiation: easy part, then 3 * hard = (x-1)^2 (x+p)(x^2+p^2-1) + 3
+// Only "product == 1" is needed, so the sign of x (a conjugation) is irrelevant.
+#pragma once
+#include "g1.cuh"
+
+namespace rk {
+
+// ---------------------------------------------------------------------------
+// strict Fq: every value <= 2p
+// ---------------------------------------------------------------------------
+template <int K>
+RK_HD void fe_cond_sub_k(Fp& a) {          // a >= K p  ?  a -= K p
+    uint32_t t[FP_N];
+    int32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < FP_N; i++) {
+        int32_t d = (int32_t)a.v[i] - (int32_t)FpTag::modx(K, i) + carry;
+        carry = d >> LIMB_BITS;
+        t[i] = (uint32_t)d & LIMB_MASK;
+    }
+    if (carry == 0) {
+#pragma unroll
+        for (int i = 0; i < FP_N; i++) a.v[i] = t[i];
+    }
+}
+RK_HD void fq_add(Fp& r, const Fp& a, const Fp& b) { fe_add(r, a, b); fe_cond_sub_k<2>(r); }
+RK_HD void fq_sub(Fp& r, const Fp& a, const Fp& b) { fe_sub<FpTag, 2>(r, a, b); fe_cond_sub_k<2>(r); }
+RK_HD void fq_neg(Fp& r, const Fp& a) { fe_neg<FpTag, 2>(r, a); }
+RK_HD void fq_dbl(Fp& r, const Fp& a) { fq_add(r, a, a); }
+RK_HD bool fq_is_zero(const Fp& a) { return fe_is_zero_mod(a); }
+RK_HD bool fq_eq(const Fp& a, const Fp& b) { Fp t; fe_sub<FpTag, 2>(t, a, b); return fe_is_zero_mod(t); }
+
+// ---------------------------------------------------------------------------
+// Fp2
+// ---------------------------------------------------------------------------
+struct Fp2 { Fp c0, c1; };
+RK_HD void fp2_add(Fp2& r, const Fp2& a, const Fp2& b) { fq_add(r.c0, a.c0, b.c0); fq_add(r.c1, a.c1, b.c1); }
+RK_HD void fp2_sub(Fp2& r, const Fp2& a, const Fp2& b) { fq_sub(r.c0, a.c0, b.c0); fq_sub(r.c1, a.c1, b.c1); }
+RK_HD void fp2_neg(Fp2& r, const Fp2& a) { fq_neg(r.c0, a.c0); fq_neg(r.c1, a.c1); }
+RK_HD void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
+    Fp v0, v1, s, t, u;
+    fe_mul(v0, a.c0, b.c0);
+    fe_mul(v1, a.c1, b.c1);
+    fq_add(s, a.c0, a.c1);
+    fq_add(t, b.c0, b.c1);
+    fe_mul(u, s, t);
+    fq_sub(u, u, v0);
+    fq_sub(r.c1, u, v1);
+    fq_sub(r.c0, v0, v1);
+}
+RK_HD void fp2_sqr(Fp2& r, const Fp2& a) {
+    Fp s, d, m;
+    fq_add(s, a.c0, a.c1);
+    fq_sub(d, a.c0, a.c1);
+    fe_mul(m, a.c0, a.c1);
+    fe_mul(r.c0, s, d);
+    fq_add(r.c1, m, m);
+}
+RK_HD void fp2_mul_fp(Fp2& r, const Fp2& a, const Fp& k) { fe_mul(r.c0, a.c0, k); fe_mul(r.c1, a.c1, k); }
+RK_HD void fp2_inv(Fp2& r, const Fp2& a) {
+    Fp n0, n1, n, ninv;
+    fe_sqr(n0, a.c0);
+    fe_sqr(n1, a.c1);
+    fq_add(n, n0, n1);
+    fe_inv(ninv, n);
+    fe_mul(r.c0, a.c0, ninv);
+    fe_mul(n0, a.c1, ninv);
+    fq_neg(r.c1, n0);
+}
+RK_HD bool fp2_is_zero(const Fp2& a) { return fq_is_zero(a.c0) && fq_is_zero(a.c1); }
+RK_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fq_eq(a.c0, b.c0) && fq_eq(a.c1, b.c1); }
+
+// ---------------------------------------------------------------------------
+// G2 (twist, affine).  inf flag explicit.
+// ---------------------------------------------------------------------------
+struct G2Affine { Fp2 x, y; int inf; };
+
+// on twist: y^2 == x^3 + 4(1+i)
+RK_HD bool g2_on_curve(const G2Affine& q) {
+    if (q.inf) return true;
+    Fp2 l, r3, b;
+    fp2_sqr(l, q.y);
+    fp2_sqr(r3, q.x);
+    fp2_mul(r3, r3, q.x);
+    fe_const<FpTag, FP_B_COEFF>(b.c0);
+    fe_const<FpTag, FP_B_COEFF>(b.c1);
+    fp2_add(r3, r3, b);
+    return fp2_eq(l, r3);
+}
+
+// ---------------------------------------------------------------------------
+// Fp12
+// ---------------------------------------------------------------------------
+struct Fp12 { Fp c[12]; };
+
+RK_HD void fp12_one(Fp12& r) {
+    for (int i = 0; i < 12; i++) fe_zero(r.c[i]);
+    fe_const<FpTag, FP_ONE>(r.c[0]);
+}
+RK_HD bool fp12_is_one(const Fp12& a) {
+    Fp one;
+    fe_const<FpTag, FP_ONE>(one);
+    bool ok = fq_eq(a.c[0], one);
+    for (int i = 1; i < 12; i++) ok = ok && fq_is_zero(a.c[i]);
+    return ok;
+}
+// reduce 23 coefficients modulo w^12 = 2 w^6 - 2
+RK_HD void fp12_fold(Fp12& r, Fp* t /* [23] */) {
+    for (int k = 22; k >= 12; k--) {
+        Fp d;
+        fq_dbl(d, t[k]);
+        fq_add(t[k - 6], t[k - 6], d);
+        fq_sub(t[k - 12], t[k - 12], d);
+    }
+    for (int k = 0; k < 12; k++) r.c[k] = t[k];
+}
+RK_HD_NOINLINE void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
+    Fp t[23];
+    for (int k = 0; k < 23; k++) fe_zero(t[k]);
+    for (int i = 0; i < 12; i++)
+        for (int j = 0; j < 12; j++) {
+            Fp m;
+            fe_mul(m, a.c[i], b.c[j]);
+            fq_add(t[i + j], t[i + j], m);
+        }
+    fp12_fold(r, t);
+}
+RK_HD void fp12_sqr(Fp12& r, const Fp12& a) { fp12_mul(r, a, a); }
+// a * (l0 + l6 w^6 + l2 w^2 + l8 w^8 + l3 w^3): the shape of a line function
+struct LineCoeffs { Fp l0, l6, l2, l8, l3; };
+RK_HD_NOINLINE void fp12_mul_line(Fp12& r, const Fp12& a, const LineCoeffs& l) {
+    Fp t[23];
+    for (int k = 0; k < 23; k++) fe_zero(t[k]);
+    for (int i = 0; i < 12; i++) {
+        Fp m;
+        fe_mul(m, a.c[i], l.l0); fq_add(t[i], t[i], m);
+        fe_mul(m, a.c[i], l.l2); fq_add(t[i + 2], t[i + 2], m);
+        fe_mul(m, a.c[i], l.l3); fq_add(t[i + 3], t[i + 3], m);
+        fe_mul(m, a.c[i], l.l6); fq_add(t[i + 6], t[i + 6], m);
+        fe_mul(m, a.c[i], l.l8); fq_add(t[i + 8], t[i + 8], m);
+    }
+    fp12_fold(r, t);
+}
+RK_HD void fp12_conj(Fp12& r, const Fp12& a) {      // Frobenius^6: w -> -w
+    for (int i = 0; i < 12; i++) {
+        if (i & 1) fq_neg(r.c[i], a.c[i]); else r.c[i] = a.c[i];
+    }
+}
+// Frobenius p^k (k = 1, 2) through the constant table FP12_FROBk
+template <class TAB>
+RK_HD_NOINLINE void fp12_frob(Fp12& r, const Fp12& a) {
+    Fp t[12];
+    for (int k = 0; k < 12; k++) fe_zero(t[k]);
+    for (int j = 0; j < 12; j++) {
+        Fp lo, hi, m;
+        for (int l = 0; l < FP_N; l++) { lo.v[l] = TAB::at(j * 26 + l); hi.v[l] = TAB::at(j * 26 + 13 + l); }
+        fe_mul(m, a.c[j], lo); fq_add(t[j % 6], t[j % 6], m);
+        fe_mul(m, a.c[j], hi); fq_add(t[j % 6 + 6], t[j % 6 + 6], m);
+    }
+    for (int k = 0; k < 12; k++) r.c[k] = t[k];
+}
+// inverse by Gauss-Jordan on the 12 x 12 multiplication matrix (used once per check)
+RK_HD_NOINLINE bool fp12_inv(Fp12& r, const Fp12& a) {
+    Fp m[12][13];
+    // column j of M = a * w^j ; solve M x = e0.  Build rows directly: M[row][col]
+    Fp12 cur = a;
+    for (int j = 0; j < 12; j++) {
+        for (int row = 0; row < 12; row++) m[row][j] = cur.c[row];
+        // cur *= w : shift up, fold w^12 = 2 w^6 - 2
+        Fp top = cur.c[11], d;
+        for (int k = 11; k >= 1; k--) cur.c[k] = cur.c[k - 1];
+        fe_zero(cur.c[0]);
+        fq_dbl(d, top);
+        fq_add(cur.c[6], cur.c[6], d);
+        fq_sub(cur.c[0], cur.c[0], d);
+    }
+    for (int row = 0; row < 12; row++) fe_zero(m[row][12]);
+    fe_const<FpTag, FP_ONE>(m[0][12]);
+    for (int col = 0; col < 12; col++) {
+        int piv = -1;
+        for (int row = col; row < 12; row++) if (!fq_is_zero(m[row][col])) { piv = row; break; }
+        if (piv < 0) return false;
+        if (piv != col) for (int k = 0; k < 13; k++) { Fp t = m[piv][k]; m[piv][k] = m[col][k]; m[col][k] = t; }
+        Fp inv;
+        fe_inv(inv, m[col][col]);
+        for (int k = col; k < 13; k++) fe_mul(m[col][k], m[col][k], inv);
+        for (int row = 0; row < 12; row++) {
+            if (row == col || fq_is_zero(m[row][col])) continue;
+            Fp f = m[row][col];
+            for (int k = col; k < 13; k++) {
+                Fp t;
+                fe_mul(t, f, m[col][k]);
+                fq_sub(m[row][k], m[row][k], t);
+            }
+        }
+    }
+    for (int k = 0; k < 12; k++) r.c[k] = m[k][12];
+    return true;
+}
+// a^|x| (plain square and multiply, 64-bit exponent)
+RK_HD_NOINLINE void fp12_pow_x(Fp12& r, const Fp12& a) {
+    Fp12 acc = a;
+    const uint64_t e = ((uint64_t)BLS_X_ABS_W32::at(1) << 32) | BLS_X_ABS_W32::at(0);
+    for (int bit = 62; bit >= 0; bit--) {
+        fp12_sqr(acc, acc);
+        if ((e >> bit) & 1) fp12_mul(acc, acc, a);
+    }
+    r = acc;
+}
+
+// f^((p^12 - 1) / r * 3) == 1 ?   (the factor 3 is coprime to r)
+RK_HD_NOINLINE bool final_exp_is_one(const Fp12& f) {
+    Fp12 inv, t, f2, a, b, c, d;
+    if (!fp12_inv(inv, f)) return false;
+    fp12_conj(t, f);
+    fp12_mul(t, t, inv);                       // f^(p^6 - 1)
+    fp12_frob<FP12_FROB2>(f2, t);
+    fp12_mul(f2, f2, t);                       // ^(p^2 + 1): now in the cyclotomic subgroup (inverse = conj)
+    // a = f2^(x-1),  x - 1 = -(|x| + 1)
+    fp12_pow_x(a, f2); fp12_mul(a, a, f2); fp12_conj(a, a);
+    fp12_pow_x(b, a);  fp12_mul(b, b, a);  fp12_conj(b, b);        // b = f2^((x-1)^2)
+    // c = b^(x + p)
+    fp12_pow_x(c, b); fp12_conj(c, c);
+    fp12_frob<FP12_FROB1>(t, b);
+    fp12_mul(c, c, t);
+    // d = c^(x^2 + p^2 - 1)
+    fp12_pow_x(d, c); fp12_pow_x(d, d);                            // x^2 > 0
+    fp12_frob<FP12_FROB2>(t, c);
+    fp12_mul(d, d, t);
+    fp12_conj(t, c);
+    fp12_mul(d, d, t);
+    // result = d * f2^3
+    fp12_sqr(t, f2);
+    fp12_mul(t, t, f2);
+    fp12_mul(d, d, t);
+    return fp12_is_one(d);
+}
+
+// ---------------------------------------------------------------------------
+// Miller loop for up to NP pairs, product of f_{|x|,Q_k}(P_k)
+// ---------------------------------------------------------------------------
+RK_HD void line_coeffs(LineCoeffs& l, const Fp2& lam, const Fp2& xt, const Fp2& yt, const Fp& xp, const Fp& yp) {
+    Fp2 c0, c2;
+    fp2_mul(c0, lam, xt);
+    fp2_sub(c0, c0, yt);                       // lam*xT - yT
+    fp2_mul_fp(c2, lam, xp);
+    fp2_neg(c2, c2);                           // -lam*xP
+    fq_sub(l.l0, c0.c0, c0.c1); l.l6 = c0.c1;  // a + b i  ->  (a - b) + b w^6
+    fq_sub(l.l2, c2.c0, c2.c1); l.l8 = c2.c1;
+    l.l3 = yp;
+}
+
+template <int NP>
+RK_HD_NOINLINE void miller_loop(Fp12& f, const G1Affine* ps, const int* p_inf, const G2Affine* qs) {
+    fp12_one(f);
+    G2Affine t[NP];
+    bool live[NP];
+    for (int k = 0; k < NP; k++) { t[k] = qs[k]; live[k] = !p_inf[k] && !qs[k].inf; }
+    const uint64_t e = ((uint64_t)BLS_X_ABS_W32::at(1) << 32) | BLS_X_ABS_W32::at(0);
+    for (int bit = 62; bit >= 0; bit--) {
+        fp12_sqr(f, f);
+        for (int k = 0; k < NP; k++) {
+            if (!live[k]) continue;
+            // tangent at T
+            Fp2 lam, num, den, x3, y3;
+            fp2_sqr(num, t[k].x);
+            fp2_add(den, num, num); fp2_add(num, den, num);        // 3 x^2
+            fp2_add(den, t[k].y, t[k].y);
+            fp2_inv(den, den);
+            fp2_mul(lam, num, den);
+            LineCoeffs l;
+            line_coeffs(l, lam, t[k].x, t[k].y, ps[k].x, ps[k].y);
+            fp12_mul_line(f, f, l);
+            fp2_sqr(x3, lam); fp2_sub(x3, x3, t[k].x); fp2_sub(x3, x3, t[k].x);
+            fp2_sub(y3, t[k].x, x3); fp2_mul(y3, lam, y3); fp2_sub(y3, y3, t[k].y);
+            t[k].x = x3; t[k].y = y3;
+        }
+        if ((e >> bit) & 1) {
+            for (int k = 0; k < NP; k++) {
+                if (!live[k]) continue;
+                Fp2 lam, num, den, x3, y3;
+                fp2_sub(num, qs[k].y, t[k].y);
+                fp2_sub(den, qs[k].x, t[k].x);
+                fp2_inv(den, den);
+                fp2_mul(lam, num, den);
+                LineCoeffs l;
+                line_coeffs(l, lam, t[k].x, t[k].y, ps[k].x, ps[k].y);
+                fp12_mul_line(f, f, l);
+                fp2_sqr(x3, lam); fp2_sub(x3, x3, t[k].x); fp2_sub(x3, x3, qs[k].x);
+                fp2_sub(y3, t[k].x, x3); fp2_mul(y3, lam, y3); fp2_sub(y3, y3, t[k].y);
+                t[k].x = x3; t[k].y = y3;
+            }
+        }
+    }
+}
+
+// prod_k e(P_k, Q_k) == 1 ?   P_k affine G1 (Montgomery, < 2p), Q_k affine G2 on the twist.
+template <int NP>
+RK_HD bool pairing_product_is_one(const G1Affine* ps, const int* p_inf, const G2Affine* qs) {
+    Fp12 f;
+    miller_loop<NP>(f, ps, p_inf, qs);
+    return final_exp_is_one(f);
+}
+
+// 48-byte big-endian canonical -> strict Montgomery
+RK_HD void fp_from_be48_mont(Fp& r, const uint8_t* in) {
+    uint32_t w[12];
+    for (int k = 0; k < 12; k++) w[k] = ((uint32_t)in[4 * (11 - k)] << 24) | ((uint32_t)in[4 * (11 - k) + 1] << 16) | ((uint32_t)in[4 * (11 - k) + 2] << 8) | in[4 * (11 - k) + 3];
+    Fp c;
+    fe_unpack<FpTag>(c, w);
+    fe_to_mont(r, c);
+}
+// 192 bytes (x.c0 | x.c1 | y.c0 | y.c1, big-endian canonical) -> G2Affine
+RK_HD void g2_from_be192(G2Affine& q, const uint8_t* in) {
+    fp_from_be48_mont(q.x.c0, in);
+    fp_from_be48_mont(q.x.c1, in + 48);
+    fp_from_be48_mont(q.y.c0, in + 96);
+    fp_from_be48_mont(q.y.c1, in + 144);
+    q.inf = 0;
+}
+RK_HD void g2_neg(G2Affine& r, const G2Affine& q) { r = q; fp2_neg(r.y, q.y); }
+
+}  // namespace rk

@@ -2,7 +2,7 @@
 // limb algorithms can be checked against Python big integers without a GPU.
 // TEST INFRASTRUCTURE: never linked into libraiko_kzg.so.
 #include <cstring>
-#include "../../raiko_b200/csrc/g1.cuh"
+#include "../../raiko_b200/csrc/pairing.cuh"
 using namespace rk;
 
 extern "C" {
@@ -46,4 +46,40 @@ int fc_g1_sum(const uint8_t* pts, int n, uint8_t* out) {
     G1Xyzz acc; g1_set_inf(acc);
     for (int i = 0; i < n; i++) { G1Affine q; int rc = g1_decompress(q, pts + 48 * i); if (rc == 1) continue; if (rc) return rc; g1_madd(acc, q.x, q.y); }
     g1_compress(out, acc); return 0; }
+
+// ---- pairing (raiko_b200/csrc/pairing.cuh) -------------------------------------------------
+static void be32_to_words(uint32_t k[8], const uint8_t* b) {
+    for (int i = 0; i < 8; i++) k[7 - i] = ((uint32_t)b[4 * i] << 24) | ((uint32_t)b[4 * i + 1] << 16) | ((uint32_t)b[4 * i + 2] << 8) | b[4 * i + 3];
+}
+// e(P1, Q1) * e(P2, Q2) == 1 ?  G1 compressed 48 B, G2 as 192 B (x.c0|x.c1|y.c0|y.c1 big-endian)
+int fc_pairing_check2(const uint8_t* p1, const uint8_t* q1, const uint8_t* p2, const uint8_t* q2) {
+    G1Affine ps[2]; int inf[2]; G2Affine qs[2];
+    int rc = g1_decompress(ps[0], p1); if (rc < 0) return -1; inf[0] = rc == 1;
+    rc = g1_decompress(ps[1], p2); if (rc < 0) return -1; inf[1] = rc == 1;
+    g2_from_be192(qs[0], q1); g2_from_be192(qs[1], q2);
+    if (!g2_on_curve(qs[0]) || !g2_on_curve(qs[1])) return -2;
+    return pairing_product_is_one<2>(ps, inf, qs) ? 1 : 0;
+}
+// verify_kzg_proof: e(C - [y]G1 + [z]proof, G2) * e(-proof, [s]G2) == 1
+int fc_verify_kzg_proof(const uint8_t* c48, const uint8_t* z32, const uint8_t* y32, const uint8_t* proof48,
+                        const uint8_t* g2_gen, const uint8_t* g2_s) {
+    G1Affine C, PI, G; int rc;
+    rc = g1_decompress(C, c48); if (rc < 0) return -1; bool c_inf = rc == 1;
+    rc = g1_decompress(PI, proof48); if (rc < 0) return -1; bool pi_inf = rc == 1;
+    fe_const<FpTag, FP_GEN_X>(G.x); fe_const<FpTag, FP_GEN_Y>(G.y);
+    uint32_t z[8], y[8];
+    be32_to_words(z, z32); be32_to_words(y, y32);
+    G1Xyzz acc, t;
+    g1_set_inf(acc);
+    if (!c_inf) g1_madd(acc, C.x, C.y);
+    g1_scalar_mul(t, G, y);
+    fe_neg<FpTag, 6>(t.y, t.y);                      // -[y]G  (t.y < 6p)
+    g1_add(acc, t);
+    if (!pi_inf) { g1_scalar_mul(t, PI, z); g1_add(acc, t); }
+    G1Affine ps[2]; int inf[2]; G2Affine qs[2];
+    inf[0] = !g1_xyzz_to_affine(ps[0], acc);
+    ps[1] = PI; fe_neg<FpTag, 2>(ps[1].y, PI.y); inf[1] = pi_inf;
+    g2_from_be192(qs[0], g2_gen); g2_from_be192(qs[1], g2_s);
+    return pairing_product_is_one<2>(ps, inf, qs) ? 1 : 0;
+}
 }
