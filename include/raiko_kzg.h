@@ -113,6 +113,20 @@ rk_status rk_compute_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, cons
                                      size_t n, uint8_t* out_proofs /* n*48 */,
                                      uint8_t* out_y /* n*32 */, uint8_t* per_blob_status);
 
+/* ---- verification (BASELINE.json configs[4]) -------------------------
+ * verify_kzg_proof_rust as the reference's tests use it (eip4844.rs:176-183):
+ * e(C - [y]G1 + [z]proof, G2) == e(proof, [s]G2).  *out_ok = 1 accept, 0 reject.  Invalid point
+ * encodings (not on the curve, not in G1) return RK_ERR_BAD_POINT, non-canonical z / y
+ * RK_ERR_NONCANONICAL_FE, like upstream's Err results.                                        */
+rk_status rk_verify_kzg_proof(rk_kzg_ctx* ctx, const uint8_t commitment[48], const uint8_t z[32],
+                              const uint8_t y[32], const uint8_t proof[48], int* out_ok);
+/* verify_blob_kzg_proof_batch (Deneb spec): per blob the EIP-4844 Fiat-Shamir challenge
+ * (NOT raiko's evaluation point), y = p(z), then one random-linear-combination check with two
+ * pairings, all on ctx device 0.  blobs may be host or device memory; commitments / proofs
+ * n*48 bytes each.                                                                            */
+rk_status rk_verify_blob_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments,
+                                         const uint8_t* proofs, size_t n, int* out_ok);
+
 /* ---- instrumentation ------------------------------------------------------------------ */
 typedef struct {
     double msm_ms;        /* sum of MSM kernel durations (CUDA events on their stream)    */

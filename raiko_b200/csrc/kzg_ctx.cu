@@ -560,6 +560,110 @@ rk_status run_batch(rk_kzg_ctx* ctx, BatchArgs a) {
     return RK_OK;
 }
 
+// ----------------------------------------------------------------------------------------
+// Verification (single device: ctx device 0)
+// ----------------------------------------------------------------------------------------
+constexpr size_t VERIFY_MAX_N = 16384;
+
+struct DevBuf {          // RAII for the scratch of one verification call
+    std::vector<void*> ptrs;
+    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> cudaError_t alloc(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T));
+        if (e == cudaSuccess) { ptrs.push_back(p); *out = (T*)p; }
+        return e;
+    }
+};
+
+// d_c, d_p: n x 48 compressed; d_z, d_y: n x 32 big-endian canonical (all on the device).
+rk_status verify_core(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, int n, const uint8_t* d_c, const uint8_t* d_p,
+                      const uint8_t* d_z, const uint8_t* d_y, int* out_ok) {
+    G1Affine *d_pts = nullptr, *d_pair = nullptr;
+    int *d_inf = nullptr, *d_pinf = nullptr, *d_flags = nullptr;
+    G1Xyzz *d_a = nullptr, *d_e = nullptr;
+    Fr *d_t = nullptr, *d_r = nullptr;
+    uint8_t* d_g2 = nullptr;
+    CUDA_TRY(buf.alloc(&d_pts, 2 * (size_t)n)); CUDA_TRY(buf.alloc(&d_inf, 2 * (size_t)n));
+    CUDA_TRY(buf.alloc(&d_a, (size_t)n)); CUDA_TRY(buf.alloc(&d_e, (size_t)n)); CUDA_TRY(buf.alloc(&d_t, (size_t)n));
+    CUDA_TRY(buf.alloc(&d_r, 1)); CUDA_TRY(buf.alloc(&d_pair, 2)); CUDA_TRY(buf.alloc(&d_pinf, 2));
+    CUDA_TRY(buf.alloc(&d_flags, 4)); CUDA_TRY(buf.alloc(&d_g2, 384));
+    cudaStream_t st = d->s_main;
+    CUDA_TRY(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), st));
+    // [s]G2 then the generator
+    CUDA_TRY(cudaMemcpyAsync(d_g2, ctx->g2_be.data() + 192, 192, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_g2 + 192, ctx->g2_be.data(), 192, cudaMemcpyHostToDevice, st));
+    k_g1_decompress_validate<<<(n + 63) / 64, 64, 0, st>>>(d_c, n, d_pts, d_inf, d_flags + 0);
+    k_g1_decompress_validate<<<(n + 63) / 64, 64, 0, st>>>(d_p, n, d_pts + n, d_inf + n, d_flags + 1);
+    k_batch_challenge<<<1, 1, 0, st>>>(d_c, d_z, d_y, d_p, n, d_r);
+    k_verify_terms<<<(n + 63) / 64, 64, 0, st>>>(d_r, d_z, d_y, d_pts, d_inf, d_pts + n, d_inf + n, n, d_a, d_e, d_t, d_flags + 2);
+    k_verify_reduce<<<1, VR_THREADS, 0, st>>>(d_a, d_e, d_t, n, d_pair, d_pinf);
+    k_pairing_check<<<1, 1, 0, st>>>(d_pair, d_pinf, d_g2, d_g2 + 192, d_flags + 3);
+    d->stats.total_launches += 6;
+    CUDA_TRY(cudaGetLastError());
+    int flags[4];
+    CUDA_TRY(cudaMemcpyAsync(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (flags[0]) return fail(RK_ERR_BAD_POINT, "commitment %d is not a valid G1 point", flags[0] - 1);
+    if (flags[1]) return fail(RK_ERR_BAD_POINT, "proof %d is not a valid G1 point", flags[1] - 1);
+    if (flags[2]) return fail(RK_ERR_NONCANONICAL_FE, "z or y of element %d is not a canonical field element", flags[2] - 1);
+    *out_ok = flags[3];
+    return RK_OK;
+}
+
+rk_status verify_blob_batch_device(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs,
+                                   size_t n, int* out_ok) {
+    DeviceCtx* d = ctx->devs[0];
+    std::lock_guard<std::mutex> lock(d->mu);
+    CUDA_TRY(cudaSetDevice(d->dev));
+    const bool blobs_dev = is_device_ptr(blobs);
+    if (blobs_dev && ((uintptr_t)blobs & 15)) return fail(RK_ERR_ARG, "device blob pointer must be 16-byte aligned");
+    DevBuf buf;
+    uint8_t *d_c = nullptr, *d_p = nullptr, *d_z = nullptr, *d_y = nullptr;
+    uint32_t* d_bad = nullptr;
+    CUDA_TRY(buf.alloc(&d_c, 48 * n)); CUDA_TRY(buf.alloc(&d_p, 48 * n));
+    CUDA_TRY(buf.alloc(&d_z, 32 * n)); CUDA_TRY(buf.alloc(&d_y, 32 * n)); CUDA_TRY(buf.alloc(&d_bad, n));
+    cudaStream_t st = d->s_main;
+    CUDA_TRY(cudaMemcpyAsync(d_c, commitments, 48 * n, cudaMemcpyDefault, st));
+    CUDA_TRY(cudaMemcpyAsync(d_p, proofs, 48 * n, cudaMemcpyDefault, st));
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t) * n, st));
+    const size_t chunk = (size_t)d->chunk;
+    for (size_t first = 0, ci = 0; first < n; first += chunk, ci++) {
+        ChunkSlot& s = d->slot[ci & 1];
+        const int cnt = (int)std::min(chunk, n - first);
+        const uint8_t* d_blobs;
+        if (blobs_dev) {
+            d_blobs = blobs + first * BLOB_BYTES;
+        } else {
+            if (!s.d_blobs) CUDA_TRY(cudaMalloc(&s.d_blobs, chunk * BLOB_BYTES));
+            if (ci >= 2) CUDA_TRY(cudaEventSynchronize(s.ev_done));        // slot free again?
+            CUDA_TRY(cudaMemcpyAsync(s.d_blobs, blobs + first * BLOB_BYTES, (size_t)cnt * BLOB_BYTES, cudaMemcpyHostToDevice, d->s_in));
+            CUDA_TRY(cudaEventRecord(s.ev_in, d->s_in));
+            CUDA_TRY(cudaStreamWaitEvent(st, s.ev_in, 0));
+            d->stats.h2d_bytes += (uint64_t)cnt * BLOB_BYTES;
+            d_blobs = s.d_blobs;
+        }
+        timer_begin(d, st, T_SHA);
+        k_sha_fs_challenge<<<(cnt + 31) / 32, 32, 0, st>>>(d_blobs, d_c + 48 * first, cnt, d_z + 32 * first);
+        timer_end(d, st);
+        FrParams fp{};
+        fp.blobs = d_blobs; fp.roots_brp = d->roots; fp.z_in = d_z + 32 * first; fp.mode = 1; fp.want_quotient = 0; fp.eval = 1;
+        fp.nblobs = cnt; fp.out_stride = 32; fp.out_x = nullptr; fp.out_y = d_y + 32 * first; fp.q_out = nullptr; fp.bad = d_bad + first;
+        timer_begin(d, st, T_FR);
+        k_fr_eval_quot<<<cnt, FR_THREADS, FR_SMEM_BYTES, st>>>(fp);
+        timer_end(d, st);
+        CUDA_TRY(cudaEventRecord(s.ev_done, st));
+    }
+    CUDA_TRY(cudaGetLastError());
+    std::vector<uint32_t> bad(n);
+    CUDA_TRY(cudaMemcpyAsync(bad.data(), d_bad, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    timers_collect(d);
+    for (size_t i = 0; i < n; i++)
+        if (bad[i]) return fail(RK_ERR_NONCANONICAL_FE, "blob %zu: Failed to deserialize blob to field elements", i);
+    return verify_core(ctx, d, buf, (int)n, d_c, d_p, d_z, d_y, out_ok);
+}
+
 rk_status check_blob_len(size_t len) {
     if (len != BLOB_BYTES) return fail(RK_ERR_BAD_LENGTH, "blob length %zu != %d", len, BLOB_BYTES);
     return RK_OK;
@@ -791,6 +895,41 @@ rk_status rk_calc_kzg_proof(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_le
     rk_status st = rk_get_evaluation_point(ctx, blob, blob_len, versioned_hash, x);
     if (st != RK_OK) return st;
     return rk_compute_kzg_proof(ctx, blob, blob_len, x, out_proof, nullptr);
+}
+
+rk_status rk_verify_kzg_proof(rk_kzg_ctx* ctx, const uint8_t commitment[48], const uint8_t z[32], const uint8_t y[32],
+                              const uint8_t proof[48], int* out_ok) {
+    if (!ctx || !commitment || !z || !y || !proof || !out_ok) return fail(RK_ERR_ARG, "null argument");
+    *out_ok = 0;
+    DeviceCtx* d = ctx->devs[0];
+    std::lock_guard<std::mutex> lock(d->mu);
+    CUDA_TRY(cudaSetDevice(d->dev));
+    DevBuf buf;
+    uint8_t* d_in = nullptr;
+    CUDA_TRY(buf.alloc(&d_in, 160));
+    uint8_t h[160];
+    memcpy(h, commitment, 48); memcpy(h + 48, proof, 48); memcpy(h + 96, z, 32); memcpy(h + 128, y, 32);
+    CUDA_TRY(cudaMemcpyAsync(d_in, h, 160, cudaMemcpyHostToDevice, d->s_main));
+    return verify_core(ctx, d, buf, 1, d_in, d_in + 48, d_in + 96, d_in + 128, out_ok);
+}
+
+rk_status rk_verify_blob_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments,
+                                         const uint8_t* proofs, size_t n, int* out_ok) {
+    if (!ctx || !out_ok) return fail(RK_ERR_ARG, "null argument");
+    *out_ok = 0;
+    if (n == 0) { *out_ok = 1; return RK_OK; }
+    if (!blobs || !commitments || !proofs) return fail(RK_ERR_ARG, "null argument");
+    // one transcript per <= 16384 blobs; larger inputs are verified as consecutive sub-batches
+    int all = 1;
+    for (size_t first = 0; first < n; first += VERIFY_MAX_N) {
+        const size_t cnt = std::min(VERIFY_MAX_N, n - first);
+        int ok = 0;
+        rk_status st = verify_blob_batch_device(ctx, blobs + first * BLOB_BYTES, commitments + 48 * first, proofs + 48 * first, cnt, &ok);
+        if (st != RK_OK) return st;
+        all &= ok;
+    }
+    *out_ok = all;
+    return RK_OK;
 }
 
 void rk_kzg_stats_enable(rk_kzg_ctx* ctx, int enable) {

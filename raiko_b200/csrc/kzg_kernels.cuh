@@ -736,3 +736,222 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint64_t* out, uint32_t seed,
 }
 
 }  // namespace rk
+
+// ===========================================================================
+// Verification (BASELINE.json configs[4]):
+// verify_kzg_proof and verify_blob_kzg_proof_batch (Deneb spec, App. B.6).
+// ===========================================================================
+#include "pairing.cuh"
+
+namespace rk {
+
+// z_i = hash_to_bls_field(sha256("FSBLOBVERIFY_V1_" | u128_be(4096) | blob | commitment)), one thread per blob.
+// The 32-byte prefix shifts the blob by half a SHA block.
+__global__ void __launch_bounds__(32) k_sha_fs_challenge(const uint8_t* blobs, const uint8_t* commitments, int nblobs,
+                                                          uint8_t* out_z) {
+    const int blob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blob >= nblobs) return;
+    const uint4* p = reinterpret_cast<const uint4*>(blobs + (size_t)blob * BLOB_BYTES);
+    const uint8_t* c = commitments + 48 * (size_t)blob;
+    Sha256State st;
+    sha256_init(st);
+    uint32_t w[16];
+    // "FSBLOBVERIFY_V1_" then 16-byte big-endian 4096
+    w[0] = 0x4653424cu; w[1] = 0x4f425645u; w[2] = 0x52494659u; w[3] = 0x5f56315fu;
+    w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 4096u;
+    uint4 v0 = ldg_nc(p), v1 = ldg_nc(p + 1);
+    w[8] = __byte_perm(v0.x, 0, 0x0123); w[9] = __byte_perm(v0.y, 0, 0x0123); w[10] = __byte_perm(v0.z, 0, 0x0123); w[11] = __byte_perm(v0.w, 0, 0x0123);
+    w[12] = __byte_perm(v1.x, 0, 0x0123); w[13] = __byte_perm(v1.y, 0, 0x0123); w[14] = __byte_perm(v1.z, 0, 0x0123); w[15] = __byte_perm(v1.w, 0, 0x0123);
+    sha256_compress(st, w);
+    for (int b = 1; b < BLOB_BYTES / 64; b++) {          // blob bytes [64b - 32, 64b + 32)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint4 v = ldg_nc(p + 4 * b - 2 + q);
+            w[4 * q] = __byte_perm(v.x, 0, 0x0123); w[4 * q + 1] = __byte_perm(v.y, 0, 0x0123);
+            w[4 * q + 2] = __byte_perm(v.z, 0, 0x0123); w[4 * q + 3] = __byte_perm(v.w, 0, 0x0123);
+        }
+        sha256_compress(st, w);
+    }
+    v0 = ldg_nc(p + BLOB_BYTES / 16 - 2); v1 = ldg_nc(p + BLOB_BYTES / 16 - 1);
+    w[0] = __byte_perm(v0.x, 0, 0x0123); w[1] = __byte_perm(v0.y, 0, 0x0123); w[2] = __byte_perm(v0.z, 0, 0x0123); w[3] = __byte_perm(v0.w, 0, 0x0123);
+    w[4] = __byte_perm(v1.x, 0, 0x0123); w[5] = __byte_perm(v1.y, 0, 0x0123); w[6] = __byte_perm(v1.z, 0, 0x0123); w[7] = __byte_perm(v1.w, 0, 0x0123);
+    for (int k = 0; k < 8; k++) w[8 + k] = load_be32(c + 4 * k);
+    sha256_compress(st, w);
+    for (int k = 0; k < 4; k++) w[k] = load_be32(c + 32 + 4 * k);
+    w[4] = 0x80000000u;
+    for (int k = 5; k < 15; k++) w[k] = 0;
+    w[15] = (uint32_t)(32 + BLOB_BYTES + 48) * 8u;
+    sha256_compress(st, w);
+    uint8_t h[32];
+    for (int i = 0; i < 8; i++) store_be32(h + 4 * i, st.h[i]);
+    Fr zm, zc;
+    fr_from_be_reduce(zm, zc, h);
+    uint32_t zw[8];
+    fe_pack<FrTag>(zw, zc);
+    uint8_t* o = out_z + 32 * (size_t)blob;
+    for (int k = 0; k < 8; k++) store_be32(o + 4 * k, zw[7 - k]);
+}
+
+// Decompress + validate (on curve, in the r-torsion) n compressed G1 points.  Infinity is
+// valid.  err[0] = 1 + index of the first bad point.
+__global__ void __launch_bounds__(64) k_g1_decompress_validate(const uint8_t* in, int n, G1Affine* out, int* out_inf, int* err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine a;
+    int rc = g1_decompress(a, in + 48 * (size_t)i);
+    if (rc < 0) { atomicCAS(err, 0, i + 1); out_inf[i] = 1; return; }
+    if (rc == 1) { out_inf[i] = 1; return; }
+    uint32_t k[8];
+    for (int w = 0; w < 8; w++) k[w] = FR_MOD_W32::at(w);
+    G1Xyzz t;
+    g1_scalar_mul(t, a, k);
+    if (!g1_is_inf(t)) { atomicCAS(err, 0, i + 1); out_inf[i] = 1; return; }
+    out[i] = a;
+    out_inf[i] = 0;
+}
+
+// 32 big-endian bytes -> canonical words; returns false when >= r
+__device__ __forceinline__ bool fr_words_from_be_canon(uint32_t (&s)[8], const uint8_t* p) {
+    for (int k = 0; k < 8; k++) s[7 - k] = load_be32(p + 4 * k);
+    return !scalar_geq_r(s);
+}
+
+// r = hash_to_bls_field(sha256("RCKZGBATCH___V1_" | be64(4096) | be64(n) | (C_i | z_i | y_i | proof_i)*)), one thread.
+__global__ void k_batch_challenge(const uint8_t* c, const uint8_t* z, const uint8_t* y, const uint8_t* pr, int n, Fr* out_r) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Sha256State st;
+    sha256_init(st);
+    uint8_t buf[64];
+    int fill = 0;
+    uint64_t total = 0;
+    auto push = [&](const uint8_t* p, int len) {
+        for (int i = 0; i < len; i++) {
+            buf[fill++] = p[i];
+            if (fill == 64) {
+                uint32_t w[16];
+                for (int k = 0; k < 16; k++) w[k] = load_be32(buf + 4 * k);
+                sha256_compress(st, w);
+                fill = 0;
+            }
+        }
+        total += (uint64_t)len;
+    };
+    const uint8_t dom[16] = {'R', 'C', 'K', 'Z', 'G', 'B', 'A', 'T', 'C', 'H', '_', '_', '_', 'V', '1', '_'};
+    uint8_t hdr[16] = {0, 0, 0, 0, 0, 0, 0x10, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 8; k++) hdr[8 + k] = (uint8_t)((uint64_t)n >> (56 - 8 * k));
+    push(dom, 16);
+    push(hdr, 16);
+    for (int i = 0; i < n; i++) {
+        push(c + 48 * (size_t)i, 48); push(z + 32 * (size_t)i, 32); push(y + 32 * (size_t)i, 32); push(pr + 48 * (size_t)i, 48);
+    }
+    const uint64_t bits = total * 8;
+    uint8_t one = 0x80, zero = 0;
+    push(&one, 1);
+    while (fill != 56) push(&zero, 1);
+    uint8_t len[8];
+    for (int k = 0; k < 8; k++) len[k] = (uint8_t)(bits >> (56 - 8 * k));
+    push(len, 8);
+    uint8_t h[32];
+    for (int i = 0; i < 8; i++) store_be32(h + 4 * i, st.h[i]);
+    Fr rm, rc;
+    fr_from_be_reduce(rm, rc, h);
+    *out_r = rm;
+}
+
+// Thread i: r^i, then  A_i = r^i * proof_i,  E_i = (r^i z_i) * proof_i + r^i * C_i,  t_i = r^i y_i.
+__global__ void __launch_bounds__(64) k_verify_terms(const Fr* r_mont, const uint8_t* z, const uint8_t* y, const G1Affine* cs,
+                                                      const int* c_inf, const G1Affine* ps, const int* p_inf, int n, G1Xyzz* out_a,
+                                                      G1Xyzz* out_e, Fr* out_t, int* err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t zw[8], yw[8];
+    if (!fr_words_from_be_canon(zw, z + 32 * (size_t)i) || !fr_words_from_be_canon(yw, y + 32 * (size_t)i)) atomicCAS(err, 0, i + 1);
+    Fr base = *r_mont, ri, zc, zm, yc, ym, t;
+    fe_const<FrTag, FR_ONE>(ri);
+    for (uint32_t e = (uint32_t)i; e; e >>= 1) {
+        if (e & 1) fe_mul(ri, ri, base);
+        fe_sqr(base, base);
+    }
+    fe_unpack<FrTag>(zc, zw); fe_to_mont(zm, zc);
+    fe_unpack<FrTag>(yc, yw); fe_to_mont(ym, yc);
+    fe_mul(t, ri, ym);
+    out_t[i] = t;
+    Fr s2, k1c, k2c;
+    fe_mul(s2, ri, zm);
+    fe_from_mont(k1c, ri);
+    fe_from_mont(k2c, s2);
+    uint32_t k1[8], k2[8];
+    fe_pack<FrTag>(k1, k1c);
+    fe_pack<FrTag>(k2, k2c);
+    G1Xyzz a, e, d;
+    g1_set_inf(a); g1_set_inf(e);
+    if (!p_inf[i]) { g1_scalar_mul(a, ps[i], k1); g1_scalar_mul(e, ps[i], k2); }
+    if (!c_inf[i]) { g1_scalar_mul(d, cs[i], k1); g1_add(e, d); }
+    out_a[i] = a;
+    out_e[i] = e;
+}
+
+// One CTA: PL = sum A_i, ER = sum E_i - (sum t_i) * G; writes the two pairing inputs
+// (-PL, ER) as affine points with infinity flags.
+constexpr int VR_THREADS = 128;
+__global__ void __launch_bounds__(VR_THREADS) k_verify_reduce(const G1Xyzz* a, const G1Xyzz* e, const Fr* t, int n, G1Affine* out_pts, int* out_inf) {
+    __shared__ G1Xyzz sh[VR_THREADS];
+    __shared__ Fr sht[VR_THREADS];
+    const int tid = threadIdx.x;
+    G1Xyzz acc;
+    for (int pass = 0; pass < 2; pass++) {
+        const G1Xyzz* src = pass == 0 ? a : e;
+        g1_set_inf(acc);
+        for (int i = tid; i < n; i += VR_THREADS) { G1Xyzz p = src[i]; g1_add(acc, p); }
+        sh[tid] = acc;
+        __syncthreads();
+        for (int s = VR_THREADS / 2; s >= 1; s >>= 1) {
+            if (tid < s) { G1Xyzz p = sh[tid + s]; G1Xyzz q = sh[tid]; g1_add(q, p); sh[tid] = q; }
+            __syncthreads();
+        }
+        if (pass == 0) {
+            if (tid == 0) {
+                G1Xyzz pl = sh[0];
+                G1Affine aff;
+                out_inf[0] = !g1_xyzz_to_affine(aff, pl);
+                if (!out_inf[0]) { fe_neg<FpTag, 2>(aff.y, aff.y); out_pts[0] = aff; }
+            }
+            __syncthreads();
+        }
+    }
+    Fr ts;
+    fe_zero(ts);
+    for (int i = tid; i < n; i += VR_THREADS) fe_add(ts, ts, t[i]);       // n * 1.1 r must stay < 2^270: n < 30 000 per call
+    sht[tid] = ts;
+    __syncthreads();
+    if (tid == 0) {
+        Fr total, tc;
+        fe_zero(total);
+        for (int k = 0; k < VR_THREADS; k++) fe_add(total, total, sht[k]);
+        fe_from_mont(tc, total);                                    // canonical sum of r^i y_i
+        uint32_t k[8];
+        fe_pack<FrTag>(k, tc);
+        G1Affine g;
+        fe_const<FpTag, FP_GEN_X>(g.x); fe_const<FpTag, FP_GEN_Y>(g.y);
+        G1Xyzz yg, er = sh[0];
+        g1_scalar_mul(yg, g, k);
+        if (!g1_is_inf(yg)) fe_neg<FpTag, 6>(yg.y, yg.y);
+        g1_add(er, yg);
+        G1Affine aff;
+        out_inf[1] = !g1_xyzz_to_affine(aff, er);
+        if (!out_inf[1]) out_pts[1] = aff;
+    }
+}
+
+// e(pts[0], [s]G2) * e(pts[1], G2) == 1 ?   Single thread.
+__global__ void k_pairing_check(const G1Affine* pts, const int* inf, const uint8_t* g2_s_be, const uint8_t* g2_gen_be, int* out_ok) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G2Affine qs[2];
+    g2_from_be192(qs[0], g2_s_be);
+    g2_from_be192(qs[1], g2_gen_be);
+    G1Affine ps[2] = {pts[0], pts[1]};
+    int pinf[2] = {inf[0], inf[1]};
+    *out_ok = pairing_product_is_one<2>(ps, pinf, qs) ? 1 : 0;
+}
+
+}  // namespace rk

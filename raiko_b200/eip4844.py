@@ -20,7 +20,7 @@ __all__ = [
     "ComputeKzgProof", "KzgSettings", "KZGSettings", "kzg_settings", "set_kzg_settings", "get_evaluation_point",
     "proof_of_equivalence", "calc_kzg_proof", "calc_kzg_proof_with_point", "calc_kzg_proof_commitment",
     "commitment_to_version_hash", "kzg_proof_to_bytes", "blob_to_kzg_commitment", "compute_kzg_proof",
-    "kzg_to_versioned_hash", "commit_batch", "commit_prove_batch", "compute_kzg_proof_batch", "BatchResult",
+    "kzg_to_versioned_hash", "verify_kzg_proof", "verify_blob_kzg_proof_batch", "commit_batch", "commit_prove_batch", "compute_kzg_proof_batch", "BatchResult",
     "DEFAULT_SETTINGS_PATH",
 ]
 
@@ -58,6 +58,8 @@ def _check(st: int):
         raise RuntimeError("raiko_b200 CUDA failure (no CPU fallback): " + msg)
     if st == _native.RK_ERR_BAD_SETTINGS:
         raise ValueError("failed to load trusted setup: " + msg)
+    if st == _native.RK_ERR_BAD_POINT:
+        raise ValueError("invalid G1 point: " + msg)
     raise ValueError("raiko_b200: status %d: %s" % (st, msg))
 
 
@@ -266,6 +268,31 @@ def kzg_proof_to_bytes(proof: bytes) -> bytes:
     if len(proof) != 48:
         raise ValueError("proof must be 48 bytes")
     return bytes(proof)
+
+
+def verify_kzg_proof(commitment: bytes, z: bytes, y: bytes, proof: bytes, settings: Optional[KzgSettings] = None) -> bool:
+    """verify_kzg_proof_rust as the reference's tests call it (eip4844.rs:176-183)."""
+    s = _s(settings)
+    if (len(commitment), len(z), len(y), len(proof)) != (48, 32, 32, 48):
+        raise ValueError("expected commitment48, z32, y32, proof48")
+    ok = ctypes.c_int(0)
+    _check(s._lib.rk_verify_kzg_proof(s._ctx, _cptr(bytes(commitment)), _cptr(bytes(z)), _cptr(bytes(y)), _cptr(bytes(proof)),
+                                      ctypes.byref(ok)))
+    return bool(ok.value)
+
+
+def verify_blob_kzg_proof_batch(blobs, commitments: Sequence[bytes], proofs: Sequence[bytes],
+                                settings: Optional[KzgSettings] = None) -> bool:
+    """verify_blob_kzg_proof_batch (Deneb spec; BASELINE.json configs[4]) on the GPU."""
+    s = _s(settings)
+    buf, n = _blobs_buf(blobs)
+    craw = b"".join(bytes(c) for c in commitments)
+    praw = b"".join(bytes(p) for p in proofs)
+    if len(craw) != 48 * n or len(praw) != 48 * n:
+        raise ValueError("need one 48-byte commitment and proof per blob")
+    ok = ctypes.c_int(0)
+    _check(s._lib.rk_verify_blob_kzg_proof_batch(s._ctx, buf.ptr, _cptr(craw), _cptr(praw), n, ctypes.byref(ok)))
+    return bool(ok.value)
 
 
 # ---------------------------------------------------------------------------------------
