@@ -73,12 +73,11 @@ struct KernelTimer {   // optional CUDA-event pair around a launch
 struct ChunkSlot {
     uint8_t* d_blobs = nullptr;     // chunk * 131072 (host-input path only)
     uint8_t* d_q = nullptr;         // chunk * 131072 quotient scalars
-    G1Xyzz* d_partials = nullptr;   // chunk * max_splits... sized for max(chunk, small-batch splits)
+    G1Xyzz* d_partials = nullptr;   // one XYZZ partial sum per MSM warp: max(chunk, 128 * 32)
     uint8_t* d_out = nullptr;       // per blob: C48 | vh32 | x32 | y32 | proof48 | hash32 | status1(+pad)
     uint8_t* d_zin = nullptr;       // chunk * 32 (compute_kzg_proof inputs)
     uint32_t* d_bad = nullptr;      // chunk
     uint8_t* h_out = nullptr;       // pinned mirror of d_out
-    uint8_t* h_in = nullptr;        // pinned staging for pageable host input (lazy)
     cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_done = nullptr, ev_out = nullptr;
     bool busy = false;
     size_t first = 0, count = 0;    // blobs of the batch this slot currently holds
@@ -98,10 +97,11 @@ struct DeviceCtx {
     int chunk = 0;
     int max_partials = 0;
     ChunkSlot slot[2];
-    uint8_t* d_status = nullptr;           // chunk (status bytes), part of d_out really
     std::mutex mu;
     int sm_count = 148;
-    int msm_variant = 255;                 // register budget of the MSM kernel (RAIKO_KZG_MSM_REGS)
+    // MSM kernel variant (RAIKO_KZG_MSM_REGS, experiments only): 255 = inlined + CTA-lockstep barrier
+    // (default, fastest), 254 = no barrier, 253 = out-of-line multiplies, 168 / 128 = register budgets
+    int msm_variant = 255;
     int warps_per_sm = 8;
     // stats
     bool stats_on = false;
@@ -158,7 +158,6 @@ void free_device(DeviceCtx* d) {
         cudaFree(s.d_blobs); cudaFree(s.d_q); cudaFree(s.d_partials); cudaFree(s.d_out);
         cudaFree(s.d_zin); cudaFree(s.d_bad);
         if (s.h_out) cudaFreeHost(s.h_out);
-        if (s.h_in) cudaFreeHost(s.h_in);
         if (s.ev_in) cudaEventDestroy(s.ev_in);
         if (s.ev_sha) cudaEventDestroy(s.ev_sha);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
