@@ -127,6 +127,15 @@ rk_status rk_verify_kzg_proof(rk_kzg_ctx* ctx, const uint8_t commitment[48], con
 rk_status rk_verify_blob_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments,
                                          const uint8_t* proofs, size_t n, int* out_ok);
 
+/* ---- blob -> tx-list byte codec (lib/src/utils.rs:85-144 decode_blob_data; "next" rank 4) ----
+ * n blobs in, per blob up to RK_BLOB_DATA_MAX decoded bytes written at out + i*RK_BLOB_DATA_STRIDE
+ * and their count in out_len[i]; an invalid blob yields length 0 (the reference returns an empty
+ * Vec).  blobs: host or device; out / out_len: both host or both device.                          */
+#define RK_BLOB_DATA_MAX 130044
+#define RK_BLOB_DATA_STRIDE 130048
+rk_status rk_decode_blob_data_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_t n, uint8_t* out,
+                                    uint32_t* out_len);
+
 /* ---- instrumentation ------------------------------------------------------------------ */
 typedef struct {
     double msm_ms;        /* sum of MSM kernel durations (CUDA events on their stream)    */

@@ -715,3 +715,89 @@ def verify_blob_kzg_proof_batch(blobs, commitments, proofs, s: Settings) -> bool
         zs.append(z)
         ys.append(evaluate_polynomial_in_evaluation_form(deserialize_blob(blob), z, s))
     return verify_kzg_proof_batch(commitments, zs, ys, proofs, s)
+
+
+# --------------------------------------------------------------------------
+# Blob -> tx-list byte codec (lib/src/utils.rs:80-179).
+# The other consumer of the 128 KiB blob: OP-style packing, 4 field elements
+# (4 x 31 bytes + 4 x 6 spare bits) -> 127 bytes per round.
+# --------------------------------------------------------------------------
+BLOB_ENCODING_VERSION = 0
+MAX_BLOB_DATA_SIZE = (4 * 31 + 3) * 1024 - 4
+
+
+def decode_blob_data(blob: bytes) -> bytes:
+    """utils.rs:85-144, statement by statement (invalid input -> empty)."""
+    if blob[1] != BLOB_ENCODING_VERSION:
+        return b""
+    output_len = (blob[2] << 16) | (blob[3] << 8) | blob[4]
+    if output_len > MAX_BLOB_DATA_SIZE:
+        return b""
+    out = bytearray(MAX_BLOB_DATA_SIZE)
+    out[0:27] = blob[5:32]
+    opos, ipos = 28, 32
+    enc = [blob[0], 0, 0, 0]
+
+    def field_element(opos, ipos):          # utils.rs:146-161
+        if blob[ipos] & 0b1100_0000:
+            return None
+        out[opos:opos + 31] = blob[ipos + 1:ipos + 32]
+        return blob[ipos], opos + 32, ipos + 32
+
+    def reassemble(opos):                   # utils.rs:163-179
+        opos -= 1
+        x = (enc[0] & 0b0011_1111) | ((enc[1] & 0b0011_0000) << 2)
+        y = (enc[1] & 0b0000_1111) | ((enc[3] & 0b0000_1111) << 4)
+        z = (enc[2] & 0b0011_1111) | ((enc[3] & 0b0011_0000) << 2)
+        out[opos - 32] = z
+        out[opos - 64] = y
+        out[opos - 96] = x
+        return opos
+
+    for k in (1, 2, 3):
+        r = field_element(opos, ipos)
+        if r is None:
+            return b""
+        enc[k], opos, ipos = r
+    opos = reassemble(opos)
+    for _ in range(1, 1024):
+        if opos < output_len:
+            for k in range(4):
+                r = field_element(opos, ipos)
+                if r is None:
+                    return b""
+                enc[k], opos, ipos = r
+            opos = reassemble(opos)
+    if any(out[output_len:]):
+        return b""
+    if any(blob[ipos:BYTES_PER_BLOB]):
+        return b""
+    return bytes(out[:output_len])
+
+
+def encode_blob_data(data: bytes) -> bytes:
+    """Inverse of decode_blob_data (the reference only decodes; this builds test inputs)."""
+    assert len(data) <= MAX_BLOB_DATA_SIZE
+    padded = bytes(data) + bytes(MAX_BLOB_DATA_SIZE - len(data))
+    blob = bytearray(BYTES_PER_BLOB)
+    n = len(data)
+    rounds = 1 if n <= 123 else 1 + (n - 123 + 126) // 127
+    for r in range(rounds):
+        base = -4 + 127 * r                 # output offset of this round's first payload byte
+        fe = [bytearray(32) for _ in range(4)]
+        for k in range(4):
+            for b in range(1, 32):
+                idx = base + 32 * k + (b - 1)
+                if 0 <= idx < MAX_BLOB_DATA_SIZE and not (r == 0 and k == 0 and b <= 4):
+                    fe[k][b] = padded[idx]
+        x, y, z = (padded[base + 31], padded[base + 63], padded[base + 95])
+        fe[0][0] = x & 0x3F
+        fe[1][0] = ((x >> 2) & 0x30) | (y & 0x0F)
+        fe[2][0] = z & 0x3F
+        fe[3][0] = ((z >> 2) & 0x30) | ((y >> 4) & 0x0F)
+        if r == 0:
+            fe[0][1] = BLOB_ENCODING_VERSION
+            fe[0][2], fe[0][3], fe[0][4] = (n >> 16) & 0xFF, (n >> 8) & 0xFF, n & 0xFF
+        for k in range(4):
+            blob[128 * r + 32 * k:128 * r + 32 * k + 32] = fe[k]
+    return bytes(blob)

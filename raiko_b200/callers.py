@@ -136,6 +136,32 @@ def blob_tx_list_hash(tx_data: bytes, blob_commitment: bytes, proof_type: Verifi
 
 
 # ---------------------------------------------------------------------------------------
+# blob -> tx-list codec (lib/src/utils.rs:85-144)
+# ---------------------------------------------------------------------------------------
+BLOB_DATA_STRIDE = 130048
+MAX_BLOB_DATA_SIZE = (4 * 31 + 3) * 1024 - 4
+
+
+def decode_blob_data_batch(blobs, settings: Optional[KzgSettings] = None) -> List[bytes]:
+    """decode_blob_data for many blobs in one launch; invalid blobs decode to b\"\" like the reference."""
+    import ctypes
+    s = settings if settings is not None else eip4844.kzg_settings()
+    buf, n = eip4844._blobs_buf(blobs)
+    out = ctypes.create_string_buffer(BLOB_DATA_STRIDE * max(n, 1))
+    lens = (ctypes.c_uint32 * max(n, 1))()
+    eip4844._check(s._lib.rk_decode_blob_data_batch(s._ctx, buf.ptr, n, out, lens))
+    raw = out.raw
+    return [raw[i * BLOB_DATA_STRIDE:i * BLOB_DATA_STRIDE + lens[i]] for i in range(n)]
+
+
+def decode_blob_data(blob: bytes, settings: Optional[KzgSettings] = None) -> bytes:
+    """utils.rs:85-144."""
+    if len(blob) != eip4844.BYTES_PER_BLOB:
+        raise ValueError("blob must be 131072 bytes")
+    return decode_blob_data_batch([blob], settings)[0]
+
+
+# ---------------------------------------------------------------------------------------
 # run_prover tail (core/src/interfaces.rs:207-219)
 # ---------------------------------------------------------------------------------------
 def kzg_proof_hex(tx_data: bytes, blob_commitment: Optional[bytes], settings: Optional[KzgSettings] = None) -> Optional[str]:

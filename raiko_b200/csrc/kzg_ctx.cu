@@ -931,6 +931,48 @@ rk_status rk_verify_blob_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, 
     return RK_OK;
 }
 
+rk_status rk_decode_blob_data_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_t n, uint8_t* out, uint32_t* out_len) {
+    if (!ctx || !out || !out_len) return fail(RK_ERR_ARG, "null argument");
+    if (n == 0) return RK_OK;
+    if (!blobs) return fail(RK_ERR_ARG, "null blobs pointer");
+    DeviceCtx* d = ctx->devs[0];
+    std::lock_guard<std::mutex> lock(d->mu);
+    CUDA_TRY(cudaSetDevice(d->dev));
+    const bool blobs_dev = is_device_ptr(blobs), out_dev = is_device_ptr(out);
+    if (out_dev != is_device_ptr(out_len)) return fail(RK_ERR_ARG, "out and out_len must both be host or both be device pointers");
+    if (blobs_dev && ((uintptr_t)blobs & 15)) return fail(RK_ERR_ARG, "device blob pointer must be 16-byte aligned");
+    const size_t chunk = (size_t)d->chunk;
+    cudaStream_t st = d->s_main;
+    DevBuf buf;
+    uint32_t* d_len = nullptr;
+    CUDA_TRY(buf.alloc(&d_len, chunk));
+    for (size_t first = 0; first < n; first += chunk) {
+        ChunkSlot& s = d->slot[0];
+        const int cnt = (int)std::min(chunk, n - first);
+        const uint8_t* d_blobs;
+        if (blobs_dev) {
+            d_blobs = blobs + first * BLOB_BYTES;
+        } else {
+            if (!s.d_blobs) CUDA_TRY(cudaMalloc(&s.d_blobs, chunk * BLOB_BYTES));
+            CUDA_TRY(cudaMemcpyAsync(s.d_blobs, blobs + first * BLOB_BYTES, (size_t)cnt * BLOB_BYTES, cudaMemcpyHostToDevice, st));
+            d->stats.h2d_bytes += (uint64_t)cnt * BLOB_BYTES;
+            d_blobs = s.d_blobs;
+        }
+        uint8_t* d_o = out_dev ? out + first * BLOBDATA_STRIDE : s.d_q;          // d_q: chunk * 131072 >= chunk * stride
+        uint32_t* d_l = out_dev ? out_len + first : d_len;
+        k_decode_blob_data<<<cnt, 256, 0, st>>>(d_blobs, cnt, d_o, d_l);
+        d->stats.total_launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (!out_dev) {
+            CUDA_TRY(cudaMemcpyAsync(out + first * BLOBDATA_STRIDE, d_o, (size_t)cnt * BLOBDATA_STRIDE, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(out_len + first, d_l, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
+            d->stats.d2h_bytes += (uint64_t)cnt * (BLOBDATA_STRIDE + 4);
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return RK_OK;
+}
+
 void rk_kzg_stats_enable(rk_kzg_ctx* ctx, int enable) {
     if (ctx) for (auto* d : ctx->devs) d->stats_on = enable != 0;
 }

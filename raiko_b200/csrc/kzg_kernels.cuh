@@ -955,3 +955,69 @@ __global__ void k_pairing_check(const G1Affine* pts, const int* inf, const uint8
 }
 
 }  // namespace rk
+
+// ===========================================================================
+// Blob -> tx-list byte codec (lib/src/utils.rs:80-179, decode_blob_data; SURVEY.md §8(f)
+// rank 4): the other consumer of the 128 KiB blob.  Pure byte shuffling, HBM-bound:
+// 4 field elements (4 x 31 payload bytes + 4 x 6 spare bits) -> 127 bytes per round.
+// One CTA per blob, one thread per round.  Invalid input -> length 0 (the reference
+// returns an empty Vec).
+// ===========================================================================
+namespace rk {
+
+constexpr int BLOBDATA_MAX = (4 * 31 + 3) * 1024 - 4;      // 130 044
+constexpr int BLOBDATA_STRIDE = 130048;                     // output bytes reserved per blob
+
+__global__ void __launch_bounds__(256) k_decode_blob_data(const uint8_t* blobs, int nblobs, uint8_t* out, uint32_t* out_len) {
+    const int blob = blockIdx.x;
+    const int tid = threadIdx.x;
+    const uint8_t* b = blobs + (size_t)blob * BLOB_BYTES;
+    uint8_t* o = out + (size_t)blob * BLOBDATA_STRIDE;
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    const int len = ((int)b[2] << 16) | ((int)b[3] << 8) | (int)b[4];
+    if (b[1] != 0 || len > BLOBDATA_MAX) {
+        if (tid == 0) out_len[blob] = 0;
+        return;
+    }
+    const int rounds = len <= 123 ? 1 : min(1024, 1 + (len - 123 + 126) / 127);
+    bool bad = false;
+    for (int r = tid; r < 1024; r += 256) {
+        const uint8_t* in = b + 128 * r;
+        if (r < rounds) {
+            const int base = -4 + 127 * r;
+            uint8_t e[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                e[k] = in[32 * k];
+                if ((r > 0 || k > 0) && (e[k] & 0xC0)) bad = true;
+                for (int bb = (r == 0 && k == 0) ? 5 : 1; bb < 32; bb++) {
+                    const int idx = base + 32 * k + bb - 1;
+                    const uint8_t v = in[32 * k + bb];
+                    if (idx < len) o[idx] = v; else if (v) bad = true;
+                }
+            }
+            const uint8_t x = (e[0] & 0x3F) | ((e[1] & 0x30) << 2);
+            const uint8_t y = (e[1] & 0x0F) | ((e[3] & 0x0F) << 4);
+            const uint8_t z = (e[2] & 0x3F) | ((e[3] & 0x30) << 2);
+            const uint8_t xyz[3] = {x, y, z};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int idx = base + 31 + 32 * k;
+                if (idx < len) o[idx] = xyz[k]; else if (xyz[k]) bad = true;
+            }
+        } else {
+            const uint4* p = reinterpret_cast<const uint4*>(in);      // unused input tail must be zero
+            uint32_t acc = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { uint4 v = ldg_nc(p + q); acc |= v.x | v.y | v.z | v.w; }
+            if (acc) bad = true;
+        }
+    }
+    if (bad) s_bad = 1;
+    __syncthreads();
+    if (tid == 0) out_len[blob] = s_bad ? 0u : (uint32_t)len;
+}
+
+}  // namespace rk

@@ -63,3 +63,29 @@ def test_kzg_proof_appended_to_proof(gpu_settings, golden):
     assert callers.kzg_proof_hex(blob, None, gpu_settings) is None
     with pytest.raises(ValueError):
         callers.kzg_proof_hex(blob, b"\x00" * 47, gpu_settings)
+
+
+def test_blob_data_codec(gpu_settings, pyoracle):
+    """lib/src/utils.rs:85-144 on the GPU vs its statement-by-statement oracle restatement."""
+    import random
+    from raiko_b200 import callers
+    o, _ = pyoracle
+    rnd = random.Random(11)
+    datas = [bytes(rnd.randrange(256) for _ in range(n)) for n in (0, 1, 27, 28, 122, 123, 124, 127, 250, 251, 5000, 130043, 130044)]
+    blobs = [o.encode_blob_data(d) for d in datas]
+    # invalid variants: wrong version, high bits set in a field element, dirty input tail, dirty output tail, length too large
+    bad = []
+    for k in range(5):
+        b = bytearray(o.encode_blob_data(b"raiko-blob-data" * 300))
+        if k == 0: b[1] = 1
+        if k == 1: b[32 * 9] |= 0x40
+        if k == 2: b[131071] = 7
+        if k == 3: b[4] -= 1
+        if k == 4: b[2] = 0xFF
+        bad.append(bytes(b))
+    rand_blob = bytes(rnd.randrange(256) for _ in range(131072))
+    allb = blobs + bad + [rand_blob, bytes(131072)]
+    got = callers.decode_blob_data_batch(allb, gpu_settings)
+    assert got == [o.decode_blob_data(b) for b in allb]
+    assert got[:len(datas)] == datas and all(g == b"" for g in got[len(datas):len(datas) + 5])
+    assert callers.decode_blob_data(blobs[10], gpu_settings) == datas[10]
