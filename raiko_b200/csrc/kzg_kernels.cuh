@@ -221,6 +221,46 @@ __global__ void __launch_bounds__(32) k_finalize(const G1Xyzz* partials, int spl
     }
 }
 
+// Latency variant for small batches (many partial sums per blob): one warp per blob, lanes sum
+// strided partials, shuffle tree, lane 0 finishes.  Same outputs as k_finalize.
+__global__ void __launch_bounds__(32) k_finalize_warp(const G1Xyzz* partials, int splits, int nblobs,
+                                                       const uint32_t* bad, uint8_t* out_g1,
+                                                       uint8_t* out_vh, uint8_t* status, int stride) {
+    const int blob = blockIdx.x;
+    const int lane = threadIdx.x;
+    uint8_t* o = out_g1 + (size_t)stride * blob;
+    if (bad != nullptr && bad[blob]) {
+        if (lane == 0) {
+            for (int i = 0; i < 48; i++) o[i] = 0;
+            if (out_vh) for (int i = 0; i < 32; i++) out_vh[(size_t)stride * blob + i] = 0;
+            if (status) status[blob] = 2;
+        }
+        return;
+    }
+    G1Xyzz acc;
+    g1_set_inf(acc);
+    for (int s = lane; s < splits; s += 32) {
+        G1Xyzz p = partials[(size_t)blob * splits + s];
+        g1_add(acc, p);
+    }
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+        G1Xyzz t;
+        shfl_fp(t.x, acc.x, delta); shfl_fp(t.y, acc.y, delta);
+        shfl_fp(t.zz, acc.zz, delta); shfl_fp(t.zzz, acc.zzz, delta);
+        if (lane < delta) g1_add(acc, t);
+    }
+    if (lane != 0) return;
+    uint8_t buf[48];
+    g1_compress(buf, acc);
+    for (int i = 0; i < 48; i++) o[i] = buf[i];
+    if (out_vh) {
+        uint8_t h[32];
+        sha256_short(buf, 48, h);
+        h[0] = 0x01;
+        for (int i = 0; i < 32; i++) out_vh[(size_t)stride * blob + i] = h[i];
+    }
+}
+
 // Blobs that failed deserialisation: zero every output of the record, set status 2.
 __global__ void k_status_only(const uint32_t* bad, int nblobs, uint8_t* rec, uint8_t* status, int stride, int zero_bytes) {
     const int blob = blockIdx.x * blockDim.x + threadIdx.x;
@@ -239,13 +279,20 @@ __global__ void __launch_bounds__(32) k_sha_blob(const uint8_t* blobs, int nblob
     const uint4* p = reinterpret_cast<const uint4*>(blobs + (size_t)blob * BLOB_BYTES);
     Sha256State st;
     sha256_init(st);
+    uint4 nx[4];                                         // next block, loaded one compression ahead
+#pragma unroll
+    for (int q = 0; q < 4; q++) nx[q] = ldg_nc(p + q);
     for (int b = 0; b < BLOB_BYTES / 64; b++) {
         uint32_t w[16];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            uint4 v = ldg_nc(p + 4 * b + q);
+            uint4 v = nx[q];
             w[4 * q] = __byte_perm(v.x, 0, 0x0123); w[4 * q + 1] = __byte_perm(v.y, 0, 0x0123);
             w[4 * q + 2] = __byte_perm(v.z, 0, 0x0123); w[4 * q + 3] = __byte_perm(v.w, 0, 0x0123);
+        }
+        if (b + 1 < BLOB_BYTES / 64) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) nx[q] = ldg_nc(p + 4 * (b + 1) + q);
         }
         sha256_compress(st, w);
     }
