@@ -77,6 +77,7 @@ struct ChunkSlot {
     G1Xyzz* d_partials = nullptr;   // one XYZZ partial sum per MSM warp: max(chunk, 128 * 32)
     uint8_t* d_out = nullptr;       // per blob: C48 | vh32 | x32 | y32 | proof48 | hash32 | status1(+pad)
     uint8_t* d_zin = nullptr;       // chunk * 32 (compute_kzg_proof inputs)
+    Fr* d_inv = nullptr;            // chunk * 4096 Fr: batch-inversion scratch of k_fr_eval_quot
     uint32_t* d_bad = nullptr;      // chunk
     uint8_t* h_out = nullptr;       // pinned mirror of d_out
     cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_done = nullptr, ev_out = nullptr;
@@ -157,7 +158,7 @@ void free_device(DeviceCtx* d) {
     cudaSetDevice(d->dev);
     for (auto& s : d->slot) {
         cudaFree(s.d_blobs); cudaFree(s.d_q); cudaFree(s.d_partials); cudaFree(s.d_out);
-        cudaFree(s.d_zin); cudaFree(s.d_bad);
+        cudaFree(s.d_zin); cudaFree(s.d_bad); cudaFree(s.d_inv);
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.ev_in) cudaEventDestroy(s.ev_in);
         if (s.ev_sha) cudaEventDestroy(s.ev_sha);
@@ -284,6 +285,7 @@ rk_status alloc_slots(DeviceCtx* d) {
         CUDA_TRY(cudaMalloc(&s.d_partials, sizeof(G1Xyzz) * (size_t)d->max_partials));
         CUDA_TRY(cudaMalloc(&s.d_out, (size_t)d->chunk * OUT_STRIDE + d->chunk));
         CUDA_TRY(cudaMalloc(&s.d_zin, (size_t)d->chunk * 32));
+        CUDA_TRY(cudaMalloc(&s.d_inv, sizeof(Fr) * (size_t)d->chunk * NPTS));
         CUDA_TRY(cudaMalloc(&s.d_bad, sizeof(uint32_t) * d->chunk));
         CUDA_TRY(cudaMallocHost(&s.h_out, (size_t)d->chunk * OUT_STRIDE + d->chunk));
         CUDA_TRY(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
@@ -476,6 +478,7 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             fp.eval = (a.mode == MODE_POINT_ONLY) ? 0 : 1;
             fp.nblobs = cnt; fp.out_x = o + OFF_X; fp.out_y = o + OFF_Y; fp.q_out = s.d_q; fp.bad = s.d_bad;
             fp.out_stride = OUT_STRIDE;
+            fp.inv_scratch = s.d_inv;
             timer_begin(d, d->s_main, T_FR);
             k_fr_eval_quot<<<cnt, FR_THREADS, FR_SMEM_BYTES, d->s_main>>>(fp);
             timer_end(d, d->s_main);
@@ -664,6 +667,7 @@ rk_status verify_blob_batch_device(rk_kzg_ctx* ctx, const uint8_t* blobs, const 
         FrParams fp{};
         fp.blobs = d_blobs; fp.roots_brp = d->roots; fp.z_in = d_z + 32 * first; fp.mode = 1; fp.want_quotient = 0; fp.eval = 1;
         fp.nblobs = cnt; fp.out_stride = 32; fp.out_x = nullptr; fp.out_y = d_y + 32 * first; fp.q_out = nullptr; fp.bad = d_bad + first;
+        fp.inv_scratch = s.d_inv;
         timer_begin(d, st, T_FR);
         k_fr_eval_quot<<<cnt, FR_THREADS, FR_SMEM_BYTES, st>>>(fp);
         timer_end(d, st);

@@ -180,7 +180,9 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
 
 // Register-budget variants of the same body (occupancy vs. spills is an empirical trade):
 //   255 regs x 8 warps/SM, 168 regs x 12 warps/SM, 128 regs x 16 warps/SM.
-__global__ void __launch_bounds__(256, 1) k_msm(MsmParams prm) { msm_body<256, 1, 1, false>(prm); }
+// 248 registers (not 255): 8 warps then leave 2048 registers per SM, enough for one k_sha_blob
+// warp to be co-resident instead of taking an SM of its own.
+__global__ void __maxnreg__(248) k_msm(MsmParams prm) { msm_body<256, 1, 1, false>(prm); }
 __global__ void __launch_bounds__(256, 1) k_msm_calls(MsmParams prm) { msm_body<256, 1, 0, true>(prm); }
 __global__ void __launch_bounds__(256, 1) k_msm_nosync(MsmParams prm) { msm_body<256, 1, 0, false>(prm); }
 __global__ void __launch_bounds__(384, 1) k_msm_r168(MsmParams prm) { msm_body<384, 1, 0, true>(prm); }
@@ -315,8 +317,8 @@ __global__ void __launch_bounds__(32) k_sha_blob(const uint8_t* blobs, int nblob
 //   q_i = (p_i - y) / (w_i - z), with the z-in-domain case (App. B.4)
 //
 // A single CTA-wide Montgomery batch inversion of (z - w_i) serves both y and q
-// (the reference inverts twice; the values are identical).  Inverses live in shared
-// memory (4096 x 36 B).  q is written in the blob's own wire format (32-byte
+// (the reference inverts twice; the values are identical).  Inverses live in a global
+// scratch array (4096 x 36 B per blob).  q is written in the blob's own wire format (32-byte
 // big-endian canonical scalars) so the same k_msm consumes it.
 // ---------------------------------------------------------------------------
 struct FrParams {
@@ -334,6 +336,7 @@ struct FrParams {
     uint8_t* out_y;             // 32 bytes per blob at out_stride (may be null)
     uint8_t* q_out;             // nblobs * 131072 (when want_quotient)
     uint32_t* bad;              // per blob: set when a field element is >= r
+    Fr* inv_scratch;            // nblobs * 4096: prefix products, then 1/(z - w_i) (L2 / HBM)
 };
 
 __device__ __forceinline__ void fr_load_be(Fr& canon, bool& geq_r, const uint8_t* p) {
@@ -366,10 +369,13 @@ __device__ __forceinline__ void fr_from_be_reduce(Fr& mont, Fr& canon, const uin
 constexpr int FR_THREADS = 256;
 constexpr int FR_PER_THREAD = NPTS / FR_THREADS;   // 16
 
-__global__ void __launch_bounds__(FR_THREADS) k_fr_eval_quot(FrParams prm) {
+__global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Fr* inv_s = reinterpret_cast<Fr*>(smem_raw);            // [4096] prefix products, then inverses
-    Fr* tot_s = inv_s + NPTS;                                // [256] per-thread totals -> inverses
+    // per-element prefix products / inverses live in global scratch (coalesced: thread t touches
+    // element k*256 + t), not in shared memory: 147 KB per blob would pin one CTA per SM and leave
+    // the SM idle during the CTA's serial inversion.
+    Fr* inv_s = prm.inv_scratch + (size_t)blockIdx.x * NPTS;
+    Fr* tot_s = reinterpret_cast<Fr*>(smem_raw);             // [256] per-thread totals -> inverses
     Fr* lane_s = tot_s + FR_THREADS;                         // [32]
     Fr* bc_s = lane_s + 32;                                  // [4] broadcast: z, y, scale, zinv
     __shared__ int s_m;                                      // index with w_m == z, or -1
@@ -551,7 +557,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_fr_eval_quot(FrParams prm) {
         }
     }
 }
-constexpr size_t FR_SMEM_BYTES = sizeof(Fr) * (NPTS + FR_THREADS + 32 + 4);
+constexpr size_t FR_SMEM_BYTES = sizeof(Fr) * (FR_THREADS + 32 + 4);
 
 // ---------------------------------------------------------------------------
 // Trusted-setup decoding
