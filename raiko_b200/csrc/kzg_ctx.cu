@@ -105,6 +105,10 @@ struct DeviceCtx {
     // (default, fastest), 254 = no barrier, 253 = out-of-line multiplies, 168 / 128 = register budgets
     int msm_variant = 255;
     int warps_per_sm = 8;
+    // Blob hashing runs on the main stream ahead of the commitment MSM.  Beside it (own stream,
+    // RAIKO_KZG_SHA_SERIAL=0) its latency-bound warps sit in the MSM's issue slots and cost the
+    // MSM 3-6 %, more than the 3.3 ms per chunk the hash takes alone.
+    bool sha_serial = true;
     // stats
     bool stats_on = false;
     std::vector<KernelTimer> timers;
@@ -270,11 +274,12 @@ rk_status build_table(DeviceCtx* d) {
 }
 
 rk_status alloc_slots(DeviceCtx* d) {
-    // chunk: blobs per pipeline stage = two full waves of one-warp-per-blob MSM work
-    // (2 x 148 SMs x 8 warps = 2368 on B200); a chunk that is not a whole number of waves
-    // idles SMs in its last wave (1024 blobs/chunk measured 13 % slower).
-    // 2 slots x (blobs + quotients) x 128 KiB each.
-    d->chunk = 2 * d->sm_count * d->warps_per_sm;
+    // chunk: blobs per pipeline stage = four full waves of one-warp-per-blob MSM work
+    // (4 x 148 SMs x 8 warps = 4736 on B200).  A chunk that is not a whole number of waves idles
+    // SMs in its last wave (1024 blobs/chunk measured 13 % slower), and the per-chunk fixed costs
+    // (hash latency, finalize, launch gaps) amortise over more blobs.
+    // 2 slots x (blobs + quotients: 128 KiB each, inversion scratch: 144 KiB) per blob = 3.8 GB.
+    d->chunk = 4 * d->sm_count * d->warps_per_sm;
     if (const char* e = getenv("RAIKO_KZG_CHUNK")) {
         int v = atoi(e);
         if (v >= 1 && v <= 16384) d->chunk = v;
@@ -303,6 +308,7 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
     CUDA_TRY(cudaGetDeviceProperties(&prop, d->dev));
     d->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("RAIKO_KZG_MSM_REGS")) d->msm_variant = atoi(e);
+    if (const char* e = getenv("RAIKO_KZG_SHA_SERIAL")) d->sha_serial = atoi(e) != 0;
     d->warps_per_sm = d->msm_variant == 128 ? 16 : d->msm_variant == 168 ? 12 : 8;
     if (prop.major < 10)
         return fail(RK_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", d->dev, prop.major, prop.minor);
@@ -451,11 +457,12 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
 
         const bool need_hash = a.mode == MODE_COMMIT_PROVE || a.mode == MODE_EVAL_ONLY || a.mode == MODE_POINT_ONLY;
         if (need_hash) {
-            CUDA_TRY(cudaStreamWaitEvent(d->s_sha, s.ev_in, 0));
-            timer_begin(d, d->s_sha, T_SHA);
-            k_sha_blob<<<(cnt + 31) / 32, 32, 0, d->s_sha>>>(d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
-            timer_end(d, d->s_sha);
-            CUDA_TRY(cudaEventRecord(s.ev_sha, d->s_sha));
+            cudaStream_t hs = d->sha_serial ? d->s_main : d->s_sha;
+            if (!d->sha_serial) CUDA_TRY(cudaStreamWaitEvent(d->s_sha, s.ev_in, 0));
+            timer_begin(d, hs, T_SHA);
+            k_sha_blob<<<(cnt + 31) / 32, 32, 0, hs>>>(d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
+            timer_end(d, hs);
+            CUDA_TRY(cudaEventRecord(s.ev_sha, hs));
         }
         int splits = 1;
         // ---- commitment ------------------------------------------------------------------
