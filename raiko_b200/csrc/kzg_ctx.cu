@@ -284,7 +284,7 @@ rk_status alloc_slots(DeviceCtx* d) {
         int v = atoi(e);
         if (v >= 1 && v <= 16384) d->chunk = v;
     }
-    d->max_partials = std::max(d->chunk, 128 * 64) * 2;
+    d->max_partials = std::max(16 * d->chunk, 128 * 128);
     for (auto& s : d->slot) {
         CUDA_TRY(cudaMalloc(&s.d_q, (size_t)d->chunk * BLOB_BYTES));
         CUDA_TRY(cudaMalloc(&s.d_partials, sizeof(G1Xyzz) * (size_t)d->max_partials));
@@ -371,6 +371,7 @@ int pick_splits_log2(const DeviceCtx* d, size_t nblobs) {
     int best = 0;
     double best_t = 1e300;
     for (int lg = 0; lg <= 7; lg++) {
+        if ((nblobs << lg) > (size_t)d->max_partials) break;          // one XYZZ partial per warp
         const double warps = (double)(nblobs << lg);
         const double waves = std::ceil(warps / slots);
         const double t = waves * (adds_per_lane / (double)(1 << lg) + 8.0);
