@@ -254,3 +254,19 @@ def test_imad_peak_microbenchmark():
     peak, clk = ctypes.c_double(), ctypes.c_double()
     assert lib.rk_measure_imad_peak(0, ctypes.byref(peak), ctypes.byref(clk)) == 0
     assert 5e12 < peak.value < 40e12
+
+
+@pytest.mark.parametrize("n", [301, 3000])
+def test_mid_size_batches_pick_many_splits(n, gpu_settings, ref):
+    """Batches between one and a few waves use up to 128 warps per blob; the partial-sum
+    buffer must hold blobs x splits entries (regression: 3968 blobs x 8 splits overflowed)."""
+    import numpy as np
+    import raiko_b200 as rk
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 256, size=(n, 4096, 32), dtype=np.uint8)
+    a[:, :, 0] %= 0x73
+    res = rk.commit_prove_batch(a, gpu_settings)
+    assert sum(res.status) == 0
+    for i in (0, n // 2, n - 1):
+        assert (res.commitments[i], res.versioned_hashes[i], res.xs[i], res.ys[i], res.proofs[i]) == ref.commit_prove(a[i].tobytes()), i
+    assert len(set(res.commitments)) == n
