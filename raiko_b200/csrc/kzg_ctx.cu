@@ -458,8 +458,10 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
 
         const bool need_hash = a.mode == MODE_COMMIT_PROVE || a.mode == MODE_EVAL_ONLY || a.mode == MODE_POINT_ONLY;
         if (need_hash) {
-            cudaStream_t hs = d->sha_serial ? d->s_main : d->s_sha;
-            if (!d->sha_serial) CUDA_TRY(cudaStreamWaitEvent(d->s_sha, s.ev_in, 0));
+            // large chunks: hash first on the main stream; small (latency-bound) batches: beside the MSM
+            const bool serial = d->sha_serial && cnt >= d->sm_count * d->warps_per_sm;
+            cudaStream_t hs = serial ? d->s_main : d->s_sha;
+            if (!serial) CUDA_TRY(cudaStreamWaitEvent(d->s_sha, s.ev_in, 0));
             timer_begin(d, hs, T_SHA);
             k_sha_blob<<<(cnt + 31) / 32, 32, 0, hs>>>(d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
             timer_end(d, hs);

@@ -1,6 +1,7 @@
 // The reference's own unit tests (lib/src/primitives/eip4844.rs:147-214), re-stated in C++ against
 // include/raiko_kzg.hpp.  Built and run by tests/test_gpu_cpp_host.py on the GPU box.
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iterator>
 #include "../../include/raiko_kzg.hpp"
@@ -12,7 +13,7 @@ static std::string hex(const uint8_t* p, size_t n) { static const char* d = "012
 int main(int argc, char** argv) {
     std::ifstream f(argv[1], std::ios::binary);
     std::vector<uint8_t> image((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-    KZGSettings settings(image, {}, 8);
+    KZGSettings settings(image, {}, argc > 2 ? atoi(argv[2]) : 8);
     // test_blob_to_kzg_commitment (eip4844.rs:147-160)
     std::vector<uint8_t> zero(131072, 0);
     auto c0 = calc_kzg_proof_commitment(settings, zero);
