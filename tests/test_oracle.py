@@ -118,3 +118,39 @@ def test_compact_setup_equals_reference_images(pyoracle, ref):
         assert s2.g1 == s.g1 and s2.g2 == s.g2 and s2.roots_brp == s.roots_brp
         blob = synthetic_blob(3)
         assert kzg_ref.RefSettings(img).commit(blob) == ref.commit(blob)
+
+
+def test_blob_data_codec_oracle_roundtrip(pyoracle):
+    """decode_blob_data restatement (lib/src/utils.rs:85-144) against an independent encoder,
+    plus the reference's rejection rules."""
+    import random
+    o, _ = pyoracle
+    rnd = random.Random(4)
+    for n in (0, 1, 26, 27, 28, 122, 123, 124, 127, 250, 251, 4096, o.MAX_BLOB_DATA_SIZE - 1, o.MAX_BLOB_DATA_SIZE):
+        d = bytes(rnd.randrange(256) for _ in range(n))
+        b = o.encode_blob_data(d)
+        assert len(b) == 131072 and o.decode_blob_data(b) == d
+        assert all(b[32 * i] < 0x40 for i in range(4096))          # every field element stays canonical
+    base = o.encode_blob_data(b"hello world" * 50)
+    for mutate in (lambda b: b.__setitem__(1, 1), lambda b: b.__setitem__(32 * 5, b[32 * 5] | 0x80),
+                   lambda b: b.__setitem__(131071, 1), lambda b: b.__setitem__(4, b[4] - 1), lambda b: b.__setitem__(2, 0xFF)):
+        m = bytearray(base)
+        mutate(m)
+        assert o.decode_blob_data(bytes(m)) == b""
+
+
+def test_call_site_host_logic():
+    """Pure host parts of raiko_b200/callers.py (no GPU): hex decoding and proof-type selection."""
+    from raiko_b200 import callers
+    assert callers.blob_to_bytes("0X0a0B") == b"\x0a\x0b" and callers.blob_to_bytes("0x0x01") == b"\x01"
+    assert callers.blob_to_bytes("xyz") == b""
+    T, B = callers.VerifierType, callers.BlobProofType
+    assert callers.get_blob_proof_type(T.SGX, B.ProofOfEquivalence) is B.ProofOfCommitment
+    assert callers.get_blob_proof_type(T.SP1, B.ProofOfCommitment) is B.ProofOfEquivalence
+    assert callers.get_blob_proof_type(T.NONE, B.ProofOfEquivalence, proof_of_equivalence_feature=False) is B.ProofOfCommitment
+    assert B.from_str("ProofOfCommitment") is B.ProofOfCommitment
+    import pytest
+    with pytest.raises(ValueError):
+        callers.calc_blob_versioned_hash("0x00")          # wrong length: "Could not create blob"
+    with pytest.raises(LookupError):
+        callers.find_tx_blob([], bytes(32))
