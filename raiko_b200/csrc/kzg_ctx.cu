@@ -102,7 +102,7 @@ struct DeviceCtx {
     std::mutex mu;
     int sm_count = 148;
     // MSM kernel variant (RAIKO_KZG_MSM_REGS, experiments only): 255 = inlined + CTA-lockstep barrier
-    // (default, fastest), 254 = no barrier, 253 = out-of-line multiplies, 168 / 128 = register budgets
+    // (default, fastest), 254 = no barrier, 253 = out-of-line multiplies, 128 = 16 warps/SM at 128 registers
     int msm_variant = 255;
     int warps_per_sm = 8;
     // Blob hashing runs on the main stream ahead of the commitment MSM.  Beside it (own stream,
@@ -309,7 +309,7 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
     d->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("RAIKO_KZG_MSM_REGS")) d->msm_variant = atoi(e);
     if (const char* e = getenv("RAIKO_KZG_SHA_SERIAL")) d->sha_serial = atoi(e) != 0;
-    d->warps_per_sm = d->msm_variant == 128 ? 16 : d->msm_variant == 168 ? 12 : 8;
+    d->warps_per_sm = d->msm_variant == 128 ? 16 : 8;
     if (prop.major < 10)
         return fail(RK_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", d->dev, prop.major, prop.minor);
     int c = window_bits;
@@ -387,8 +387,7 @@ void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint3
     p.partials = s.d_partials; p.bad = bad;
     const long long warps = (long long)n << p.splits_log2;
     timer_begin(d, d->s_main, T_MSM);
-    if (d->msm_variant == 168) k_msm_r168<<<(unsigned)((warps + 11) / 12), 384, 0, d->s_main>>>(p);
-    else if (d->msm_variant == 128) k_msm_r128<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
+    if (d->msm_variant == 128) k_msm_r128<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
     else if (d->msm_variant == 253) k_msm_calls<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
     else if (d->msm_variant == 254) k_msm_nosync<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
     else k_msm<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);

@@ -178,14 +178,16 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
 }
 
 
-// Register-budget variants of the same body (occupancy vs. spills is an empirical trade):
-//   255 regs x 8 warps/SM, 168 regs x 12 warps/SM, 128 regs x 16 warps/SM.
+// Variants of the same body kept for A/B measurements (RAIKO_KZG_MSM_REGS): measured on B200,
+// 8 warps/SM x 248 registers with the lockstep barrier is the fastest (2.35 G additions/s);
+// 12 warps x 168 registers 2.2-2.3, 16 warps x 128 registers 2.2, no barrier 1.94,
+// out-of-line multiplies 1.92 (profiles/r01/).
 // 248 registers (not 255): 8 warps then leave 2048 registers per SM, enough for one k_sha_blob
 // warp to be co-resident instead of taking an SM of its own.
 __global__ void __maxnreg__(248) k_msm(MsmParams prm) { msm_body<256, 1, 1, false>(prm); }
 __global__ void __launch_bounds__(256, 1) k_msm_calls(MsmParams prm) { msm_body<256, 1, 0, true>(prm); }
 __global__ void __launch_bounds__(256, 1) k_msm_nosync(MsmParams prm) { msm_body<256, 1, 0, false>(prm); }
-__global__ void __launch_bounds__(384, 1) k_msm_r168(MsmParams prm) { msm_body<384, 1, 0, true>(prm); }
+
 __global__ void __launch_bounds__(256, 2) k_msm_r128(MsmParams prm) { msm_body<256, 2, 0, true>(prm); }
 
 // ---------------------------------------------------------------------------
