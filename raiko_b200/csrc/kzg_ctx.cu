@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -117,7 +119,27 @@ struct DeviceCtx {
 
 }  // namespace
 
+// One single-blob request waiting to be merged into a batch (see submit_single).
+struct SingleReq {
+    int mode = 0;
+    const uint8_t* blob = nullptr;
+    const uint8_t* aux32 = nullptr;        // z (MODE_PROOF_AT_Z) or versioned hash
+    uint8_t c[48], vh[32], x[32], y[32], proof[48];
+    uint8_t status = 0;
+    rk_status rc = RK_OK;
+    std::string err;
+    bool done = false;
+};
+
 struct rk_kzg_ctx {
+    // Concurrent single-blob callers (the reference keeps up to 16 requests in flight,
+    // host/src/proof.rs:121) are merged: the first caller becomes the leader and runs every
+    // queued request of the same kind as ONE batch; the others wait for their result.
+    std::mutex coal_mu;
+    std::condition_variable coal_cv;
+    std::deque<SingleReq*> coal_q;
+    bool coal_leader = false;
+    uint64_t coal_batches = 0, coal_requests = 0;
     std::vector<DeviceCtx*> devs;
     TableGeom geom{};
     std::vector<uint8_t> g2_be;            // 65 * 192 bytes (x.c0|x.c1|y.c0|y.c1 big-endian canonical)
@@ -348,14 +370,15 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
 // ----------------------------------------------------------------------------------------
 // Batch pipeline on one device
 // ----------------------------------------------------------------------------------------
-enum BatchMode { MODE_COMMIT = 0, MODE_COMMIT_PROVE = 1, MODE_PROOF_AT_Z = 2, MODE_EVAL_ONLY = 3, MODE_POINT_ONLY = 4 };
+enum BatchMode { MODE_COMMIT = 0, MODE_COMMIT_PROVE = 1, MODE_PROOF_AT_Z = 2, MODE_EVAL_ONLY = 3, MODE_POINT_ONLY = 4,
+                 MODE_PROVE_VH = 5 /* calc_kzg_proof: challenge from (blob, vh), then the proof */ };
 
 struct BatchArgs {
     BatchMode mode;
     const uint8_t* blobs;        // shard base (host or device)
     bool blobs_on_device;
     const uint8_t* zs;           // MODE_PROOF_AT_Z: host, n*32
-    const uint8_t* vhs;          // MODE_EVAL_ONLY / MODE_POINT_ONLY: host, n*32
+    const uint8_t* vhs;          // MODE_EVAL_ONLY / MODE_POINT_ONLY / MODE_PROVE_VH: host, n*32
     size_t n;
     uint8_t *out_c, *out_vh, *out_x, *out_y, *out_proof, *status;   // host or device, may be null
     bool outs_on_device;
@@ -445,7 +468,7 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
         }
         uint8_t* o = s.d_out;
         uint8_t* o_stat = s.d_out + chunk * OUT_STRIDE;
-        if (a.mode == MODE_EVAL_ONLY || a.mode == MODE_POINT_ONLY) {
+        if (a.mode == MODE_EVAL_ONLY || a.mode == MODE_POINT_ONLY || a.mode == MODE_PROVE_VH) {
             // caller-supplied versioned hashes go where the commit stage would have put them
             CUDA_TRY(cudaMemcpy2DAsync(o + OFF_VH, OUT_STRIDE, a.vhs + 32 * first, 32, 32, (size_t)cnt,
                                        cudaMemcpyHostToDevice, d->s_in));
@@ -455,7 +478,7 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
         CUDA_TRY(cudaMemsetAsync(s.d_bad, 0, sizeof(uint32_t) * cnt, d->s_main));
         CUDA_TRY(cudaMemsetAsync(o_stat, 0, (size_t)cnt, d->s_main));
 
-        const bool need_hash = a.mode == MODE_COMMIT_PROVE || a.mode == MODE_EVAL_ONLY || a.mode == MODE_POINT_ONLY;
+        const bool need_hash = a.mode == MODE_COMMIT_PROVE || a.mode == MODE_EVAL_ONLY || a.mode == MODE_POINT_ONLY || a.mode == MODE_PROVE_VH;
         if (need_hash) {
             // large chunks: hash first on the main stream; small (latency-bound) batches: beside the MSM
             const bool serial = d->sha_serial && cnt >= d->sm_count * d->warps_per_sm;
@@ -483,7 +506,7 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             fp.blobs = d_blobs; fp.roots_brp = d->roots;
             fp.blob_hash = o + OFF_HASH; fp.vh = o + OFF_VH; fp.z_in = s.d_zin;
             fp.mode = (a.mode == MODE_PROOF_AT_Z) ? 1 : 0;
-            fp.want_quotient = (a.mode == MODE_COMMIT_PROVE || a.mode == MODE_PROOF_AT_Z) ? 1 : 0;
+            fp.want_quotient = (a.mode == MODE_COMMIT_PROVE || a.mode == MODE_PROOF_AT_Z || a.mode == MODE_PROVE_VH) ? 1 : 0;
             fp.eval = (a.mode == MODE_POINT_ONLY) ? 0 : 1;
             fp.nblobs = cnt; fp.out_x = o + OFF_X; fp.out_y = o + OFF_Y; fp.q_out = s.d_q; fp.bad = s.d_bad;
             fp.out_stride = OUT_STRIDE;
@@ -862,67 +885,139 @@ rk_status rk_compute_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, cons
     return run_batch(ctx, a);
 }
 
+// Run `r` through the batch pipeline, merged with whatever other single-blob requests of the
+// same mode are waiting.  Blocks until r is done.
+static rk_status submit_single(rk_kzg_ctx* ctx, SingleReq& r) {
+    constexpr size_t MAX_MERGE = 64;
+    std::unique_lock<std::mutex> lk(ctx->coal_mu);
+    ctx->coal_q.push_back(&r);
+    if (ctx->coal_leader) {
+        ctx->coal_cv.wait(lk, [&] { return r.done; });
+    } else {
+        ctx->coal_leader = true;
+        while (!ctx->coal_q.empty()) {
+            std::vector<SingleReq*> batch;
+            const int mode = ctx->coal_q.front()->mode;
+            for (auto it = ctx->coal_q.begin(); it != ctx->coal_q.end() && batch.size() < MAX_MERGE;) {
+                if ((*it)->mode == mode) { batch.push_back(*it); it = ctx->coal_q.erase(it); } else ++it;
+            }
+            ctx->coal_batches++;
+            ctx->coal_requests += batch.size();
+            lk.unlock();
+            const size_t k = batch.size();
+            rk_status rc;
+            std::string err;
+            std::vector<uint8_t> st(k, 0), oc(48 * k), ovh(32 * k), ox(32 * k), oy(32 * k), op(48 * k), aux(32 * k);
+            {
+                // a lone request is passed through without the staging copy
+                std::vector<uint8_t> staged;
+                const uint8_t* blobs = batch[0]->blob;
+                if (k > 1) {
+                    staged.resize(k * (size_t)BLOB_BYTES);
+                    for (size_t i = 0; i < k; i++) memcpy(staged.data() + i * BLOB_BYTES, batch[i]->blob, BLOB_BYTES);
+                    blobs = staged.data();
+                }
+                for (size_t i = 0; i < k; i++) if (batch[i]->aux32) memcpy(aux.data() + 32 * i, batch[i]->aux32, 32);
+                BatchArgs a{};
+                a.mode = (BatchMode)mode; a.blobs = blobs; a.n = k; a.status = st.data();
+                if (mode == MODE_PROOF_AT_Z) a.zs = aux.data(); else a.vhs = aux.data();
+                if (mode == MODE_COMMIT) { a.out_c = oc.data(); a.out_vh = ovh.data(); }
+                if (mode == MODE_PROOF_AT_Z) { a.out_proof = op.data(); a.out_y = oy.data(); }
+                if (mode == MODE_EVAL_ONLY) { a.out_x = ox.data(); a.out_y = oy.data(); }
+                if (mode == MODE_POINT_ONLY) { a.out_x = ox.data(); }
+                if (mode == MODE_PROVE_VH) { a.out_x = ox.data(); a.out_y = oy.data(); a.out_proof = op.data(); }
+                rc = run_batch(ctx, a);
+                if (rc != RK_OK) err = g_last_error;
+            }
+            lk.lock();
+            for (size_t i = 0; i < k; i++) {
+                SingleReq* q = batch[i];
+                q->rc = rc; q->err = err; q->status = st[i];
+                memcpy(q->c, oc.data() + 48 * i, 48); memcpy(q->vh, ovh.data() + 32 * i, 32);
+                memcpy(q->x, ox.data() + 32 * i, 32); memcpy(q->y, oy.data() + 32 * i, 32);
+                memcpy(q->proof, op.data() + 48 * i, 48);
+                q->done = true;
+            }
+            ctx->coal_cv.notify_all();
+        }
+        ctx->coal_leader = false;
+    }
+    if (r.rc != RK_OK) g_last_error = r.err;
+    return r.rc;
+}
+
 static rk_status single_status(uint8_t st) {
     if (st == 0) return RK_OK;
     return fail((rk_status)st, "Failed to deserialize blob to field elements");
 }
 
 rk_status rk_blob_to_kzg_commitment(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, uint8_t out_commitment[48]) {
+    if (!ctx || !blob || !out_commitment) return fail(RK_ERR_ARG, "null argument");
     rk_status st = check_blob_len(blob_len);
     if (st != RK_OK) return st;
-    uint8_t c[48], s = 0;
-    st = rk_commit_batch(ctx, blob, 1, c, nullptr, &s);
+    SingleReq r;
+    r.mode = MODE_COMMIT; r.blob = blob;
+    st = submit_single(ctx, r);
     if (st != RK_OK) return st;
-    if (s) return single_status(s);
-    memcpy(out_commitment, c, 48);
+    if (r.status) return single_status(r.status);
+    memcpy(out_commitment, r.c, 48);
     return RK_OK;
 }
 
 rk_status rk_get_evaluation_point(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, const uint8_t versioned_hash[32],
                                   uint8_t out_x[32]) {
+    if (!ctx || !blob || !versioned_hash || !out_x) return fail(RK_ERR_ARG, "null argument");
     rk_status st = check_blob_len(blob_len);
     if (st != RK_OK) return st;
-    if (!versioned_hash || !out_x) return fail(RK_ERR_ARG, "null argument");
-    BatchArgs a{};
-    a.mode = MODE_POINT_ONLY; a.blobs = blob; a.vhs = versioned_hash; a.n = 1; a.out_x = out_x;
-    return run_batch(ctx, a);   // no deserialisation on this path in the reference either
+    SingleReq r;
+    r.mode = MODE_POINT_ONLY; r.blob = blob; r.aux32 = versioned_hash;
+    st = submit_single(ctx, r);          // no deserialisation on this path in the reference either
+    if (st != RK_OK) return st;
+    memcpy(out_x, r.x, 32);
+    return RK_OK;
 }
 
 rk_status rk_proof_of_equivalence(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, const uint8_t versioned_hash[32],
                                   uint8_t out_x[32], uint8_t out_y[32]) {
+    if (!ctx || !blob || !versioned_hash || !out_x || !out_y) return fail(RK_ERR_ARG, "null argument");
     rk_status st = check_blob_len(blob_len);
     if (st != RK_OK) return st;
-    if (!versioned_hash || !out_x || !out_y) return fail(RK_ERR_ARG, "null argument");
-    uint8_t x[32], y[32], s = 0;
-    BatchArgs a{};
-    a.mode = MODE_EVAL_ONLY; a.blobs = blob; a.vhs = versioned_hash; a.n = 1; a.out_x = x; a.out_y = y; a.status = &s;
-    st = run_batch(ctx, a);
+    SingleReq r;
+    r.mode = MODE_EVAL_ONLY; r.blob = blob; r.aux32 = versioned_hash;
+    st = submit_single(ctx, r);
     if (st != RK_OK) return st;
-    if (s) return single_status(s);
-    memcpy(out_x, x, 32); memcpy(out_y, y, 32);
+    if (r.status) return single_status(r.status);
+    memcpy(out_x, r.x, 32); memcpy(out_y, r.y, 32);
     return RK_OK;
 }
 
 rk_status rk_compute_kzg_proof(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, const uint8_t z[32],
                                uint8_t out_proof[48], uint8_t out_y[32]) {
+    if (!ctx || !blob || !z || !out_proof) return fail(RK_ERR_ARG, "null argument");
     rk_status st = check_blob_len(blob_len);
     if (st != RK_OK) return st;
-    if (!z || !out_proof) return fail(RK_ERR_ARG, "null argument");
-    uint8_t p[48], y[32], s = 0;
-    st = rk_compute_kzg_proof_batch(ctx, blob, z, 1, p, y, &s);
+    SingleReq r;
+    r.mode = MODE_PROOF_AT_Z; r.blob = blob; r.aux32 = z;
+    st = submit_single(ctx, r);
     if (st != RK_OK) return st;
-    if (s) return single_status(s);
-    memcpy(out_proof, p, 48);
-    if (out_y) memcpy(out_y, y, 32);
+    if (r.status) return single_status(r.status);
+    memcpy(out_proof, r.proof, 48);
+    if (out_y) memcpy(out_y, r.y, 32);
     return RK_OK;
 }
 
 rk_status rk_calc_kzg_proof(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len, const uint8_t versioned_hash[32],
                             uint8_t out_proof[48]) {
-    uint8_t x[32];
-    rk_status st = rk_get_evaluation_point(ctx, blob, blob_len, versioned_hash, x);
+    if (!ctx || !blob || !versioned_hash || !out_proof) return fail(RK_ERR_ARG, "null argument");
+    rk_status st = check_blob_len(blob_len);
     if (st != RK_OK) return st;
-    return rk_compute_kzg_proof(ctx, blob, blob_len, x, out_proof, nullptr);
+    SingleReq r;                          // one pass: hash -> challenge -> evaluation -> quotient -> MSM
+    r.mode = MODE_PROVE_VH; r.blob = blob; r.aux32 = versioned_hash;
+    st = submit_single(ctx, r);
+    if (st != RK_OK) return st;
+    if (r.status) return single_status(r.status);
+    memcpy(out_proof, r.proof, 48);
+    return RK_OK;
 }
 
 rk_status rk_verify_kzg_proof(rk_kzg_ctx* ctx, const uint8_t commitment[48], const uint8_t z[32], const uint8_t y[32],

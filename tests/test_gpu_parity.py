@@ -270,3 +270,39 @@ def test_mid_size_batches_pick_many_splits(n, gpu_settings, ref):
     for i in (0, n // 2, n - 1):
         assert (res.commitments[i], res.versioned_hashes[i], res.xs[i], res.ys[i], res.proofs[i]) == ref.commit_prove(a[i].tobytes()), i
     assert len(set(res.commitments)) == n
+
+
+def test_concurrent_single_blob_calls_are_merged(gpu_settings, golden):
+    """16 in-flight single-blob requests (host/src/proof.rs:121) must all get their own correct
+    answer; the library merges waiting requests of one kind into one batch."""
+    import threading
+    import time
+    import raiko_b200 as rk
+    cases = golden["cases"]
+    blobs = [blob_from_recipe(c["recipe"]) for c in cases]
+    rk.calc_kzg_proof_commitment(blobs[0], gpu_settings)          # warm
+    t0 = time.perf_counter()
+    for i in range(16):
+        rk.calc_kzg_proof_commitment(blobs[i % len(blobs)], gpu_settings)
+    serial = time.perf_counter() - t0
+    out, errs = [None] * 32, []
+
+    def work(k):
+        try:
+            i = k % len(blobs)
+            if k % 2 == 0:
+                out[k] = ("c", i, rk.calc_kzg_proof_commitment(blobs[i], gpu_settings))
+            else:
+                out[k] = ("p", i, rk.calc_kzg_proof(blobs[i], bytes.fromhex(cases[i]["versioned_hash"]), gpu_settings))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(32)]
+    t0 = time.perf_counter()
+    [t.start() for t in th]
+    [t.join() for t in th]
+    merged = time.perf_counter() - t0
+    assert not errs, errs
+    for kind, i, val in out:
+        want = cases[i]["commitment"] if kind == "c" else cases[i]["proofs"][0]["proof"]
+        assert val.hex() == want
+    print("16 serial commitments %.1f ms; 32 concurrent mixed calls %.1f ms" % (serial * 1e3, merged * 1e3))
