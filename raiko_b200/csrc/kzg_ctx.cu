@@ -885,10 +885,47 @@ rk_status rk_compute_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, cons
     return run_batch(ctx, a);
 }
 
+// Execute a group of same-mode single-blob requests as one batch and fill in their results.
+static void exec_requests(rk_kzg_ctx* ctx, const std::vector<SingleReq*>& batch) {
+    const size_t k = batch.size();
+    const int mode = batch[0]->mode;
+    std::vector<uint8_t> st(k, 0), oc(48 * k), ovh(32 * k), ox(32 * k), oy(32 * k), op(48 * k), aux(32 * k), staged;
+    const uint8_t* blobs = batch[0]->blob;            // a lone request is passed through without a staging copy
+    if (k > 1) {
+        staged.resize(k * (size_t)BLOB_BYTES);
+        for (size_t i = 0; i < k; i++) memcpy(staged.data() + i * BLOB_BYTES, batch[i]->blob, BLOB_BYTES);
+        blobs = staged.data();
+    }
+    for (size_t i = 0; i < k; i++) if (batch[i]->aux32) memcpy(aux.data() + 32 * i, batch[i]->aux32, 32);
+    BatchArgs a{};
+    a.mode = (BatchMode)mode; a.blobs = blobs; a.n = k; a.status = st.data();
+    if (mode == MODE_PROOF_AT_Z) a.zs = aux.data(); else a.vhs = aux.data();
+    if (mode == MODE_COMMIT) { a.out_c = oc.data(); a.out_vh = ovh.data(); }
+    if (mode == MODE_PROOF_AT_Z) { a.out_proof = op.data(); a.out_y = oy.data(); }
+    if (mode == MODE_EVAL_ONLY) { a.out_x = ox.data(); a.out_y = oy.data(); }
+    if (mode == MODE_POINT_ONLY) { a.out_x = ox.data(); }
+    if (mode == MODE_PROVE_VH) { a.out_x = ox.data(); a.out_y = oy.data(); a.out_proof = op.data(); }
+    const rk_status rc = run_batch(ctx, a);
+    const std::string err = rc != RK_OK ? g_last_error : std::string();
+    for (size_t i = 0; i < k; i++) {
+        SingleReq* q = batch[i];
+        q->rc = rc; q->err = err; q->status = st[i];
+        memcpy(q->c, oc.data() + 48 * i, 48); memcpy(q->vh, ovh.data() + 32 * i, 32);
+        memcpy(q->x, ox.data() + 32 * i, 32); memcpy(q->y, oy.data() + 32 * i, 32);
+        memcpy(q->proof, op.data() + 48 * i, 48);
+    }
+}
+
 // Run `r` through the batch pipeline, merged with whatever other single-blob requests of the
 // same mode are waiting.  Blocks until r is done.
 static rk_status submit_single(rk_kzg_ctx* ctx, SingleReq& r) {
     constexpr size_t MAX_MERGE = 64;
+    cudaSetDevice(ctx->devs[0]->dev);
+    if (is_device_ptr(r.blob)) {                       // device-resident blob: nothing to stage, run alone
+        exec_requests(ctx, {&r});
+        if (r.rc != RK_OK) g_last_error = r.err;
+        return r.rc;
+    }
     std::unique_lock<std::mutex> lk(ctx->coal_mu);
     ctx->coal_q.push_back(&r);
     if (ctx->coal_leader) {
@@ -904,40 +941,9 @@ static rk_status submit_single(rk_kzg_ctx* ctx, SingleReq& r) {
             ctx->coal_batches++;
             ctx->coal_requests += batch.size();
             lk.unlock();
-            const size_t k = batch.size();
-            rk_status rc;
-            std::string err;
-            std::vector<uint8_t> st(k, 0), oc(48 * k), ovh(32 * k), ox(32 * k), oy(32 * k), op(48 * k), aux(32 * k);
-            {
-                // a lone request is passed through without the staging copy
-                std::vector<uint8_t> staged;
-                const uint8_t* blobs = batch[0]->blob;
-                if (k > 1) {
-                    staged.resize(k * (size_t)BLOB_BYTES);
-                    for (size_t i = 0; i < k; i++) memcpy(staged.data() + i * BLOB_BYTES, batch[i]->blob, BLOB_BYTES);
-                    blobs = staged.data();
-                }
-                for (size_t i = 0; i < k; i++) if (batch[i]->aux32) memcpy(aux.data() + 32 * i, batch[i]->aux32, 32);
-                BatchArgs a{};
-                a.mode = (BatchMode)mode; a.blobs = blobs; a.n = k; a.status = st.data();
-                if (mode == MODE_PROOF_AT_Z) a.zs = aux.data(); else a.vhs = aux.data();
-                if (mode == MODE_COMMIT) { a.out_c = oc.data(); a.out_vh = ovh.data(); }
-                if (mode == MODE_PROOF_AT_Z) { a.out_proof = op.data(); a.out_y = oy.data(); }
-                if (mode == MODE_EVAL_ONLY) { a.out_x = ox.data(); a.out_y = oy.data(); }
-                if (mode == MODE_POINT_ONLY) { a.out_x = ox.data(); }
-                if (mode == MODE_PROVE_VH) { a.out_x = ox.data(); a.out_y = oy.data(); a.out_proof = op.data(); }
-                rc = run_batch(ctx, a);
-                if (rc != RK_OK) err = g_last_error;
-            }
+            exec_requests(ctx, batch);
             lk.lock();
-            for (size_t i = 0; i < k; i++) {
-                SingleReq* q = batch[i];
-                q->rc = rc; q->err = err; q->status = st[i];
-                memcpy(q->c, oc.data() + 48 * i, 48); memcpy(q->vh, ovh.data() + 32 * i, 32);
-                memcpy(q->x, ox.data() + 32 * i, 32); memcpy(q->y, oy.data() + 32 * i, 32);
-                memcpy(q->proof, op.data() + 48 * i, 48);
-                q->done = true;
-            }
+            for (SingleReq* q : batch) q->done = true;
             ctx->coal_cv.notify_all();
         }
         ctx->coal_leader = false;
