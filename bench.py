@@ -148,6 +148,16 @@ def synth_blobs_host(n: int, seed: int):
     return a
 
 
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_commit_prove(blobs, threads: int):
     """Runs kzgref_commit_prove over `blobs` (list of bytes) on `threads` host threads.
     Returns (seconds, results)."""
@@ -185,7 +195,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "u64 limbs (Fp 381-bit / Fr 255-bit Montgomery)", "data": "synthetic",
         "config": {"workload": "commit+versioned_hash+challenge+eval+proof per blob (bounded sample of the 65,536-blob batch)",
                    "blobs_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -359,7 +369,7 @@ def run_ours(args):
         dt1, _ = cpu_commit_prove(sample[:4], 1)
         cpu = {"value": ncpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d blobs of the timed batch, one blob per thread on %d threads (oracle/kzg_ref.c)" % (ncpu, cores),
-               "single_thread_value": 4 / dt1}
+               "single_thread_value": 4 / dt1, "cpu_model": cpu_model()}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -64,7 +64,8 @@ uint64_t rk_kzg_ctx_table_bytes(const rk_kzg_ctx* ctx);
  * 1 = bincode (1 001 905 B).  *len in: capacity, out: bytes written.                  */
 rk_status rk_kzg_ctx_export_settings(rk_kzg_ctx* ctx, int kind, uint8_t* out, size_t* len);
 
-/* ---- single-blob drop-ins (each call is independent and thread-safe) ------------------ */
+/* ---- single-blob drop-ins (thread-safe; calls that arrive while the device is busy are
+ * merged into one batch per kind, so 16 concurrent requests cost about one) --------------- */
 /* calc_kzg_proof_commitment (eip4844.rs:80-89) / blob_to_kzg_commitment_rust             */
 rk_status rk_blob_to_kzg_commitment(rk_kzg_ctx* ctx, const uint8_t* blob, size_t blob_len,
                                     uint8_t out_commitment[48]);
