@@ -485,7 +485,10 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             cudaStream_t hs = serial ? d->s_main : d->s_sha;
             if (!serial) CUDA_TRY(cudaStreamWaitEvent(d->s_sha, s.ev_in, 0));
             timer_begin(d, hs, T_SHA);
-            k_sha_blob<<<(cnt + 31) / 32, 32, 0, hs>>>(d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
+            // <= 8 blobs (a Cancun block has <= 6): the MSM leaves SMs free, use the two-warp hash.
+            // Larger batches keep the one-warp kernel, whose 2048 registers fit beside an MSM CTA.
+            if (cnt <= 8) k_sha_blob_duo<<<cnt, 64, 0, hs>>>(d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
+            else k_sha_blob<<<(cnt + 31) / 32, 32, 0, hs>>>(d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
             timer_end(d, hs);
             CUDA_TRY(cudaEventRecord(s.ev_sha, hs));
         }

@@ -59,6 +59,36 @@ RK_HD void sha256_compress(Sha256State& s, uint32_t (&w)[16]) {
     s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
 
+// The two halves of a compression, for the latency-oriented two-warp hash (k_sha_blob_duo):
+// message schedule (no dependence on the chaining state) and the 64 rounds.
+RK_HD void sha256_schedule(uint32_t* wout /* [64] */, const uint32_t (&blk)[16]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { w[i] = blk[i]; wout[i] = blk[i]; }
+#pragma unroll
+    for (int i = 16; i < 64; i++) {
+        uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+        uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+        uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+        w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+        wout[i] = w[i & 15];
+    }
+}
+RK_HD void sha256_rounds(Sha256State& s, const uint32_t* w /* [64], expanded */) {
+    uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = h + S1 + ch + SHA256_K::at(i) + w[i];
+        uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+}
+
 RK_HD uint32_t load_be32(const uint8_t* p) {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
 }
