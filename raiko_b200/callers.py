@@ -136,6 +136,68 @@ def blob_tx_list_hash(tx_data: bytes, blob_commitment: bytes, proof_type: Verifi
 
 
 # ---------------------------------------------------------------------------------------
+# instance_hash (lib/src/protocol_instance.rs:165-185): where (x, y) end up
+# ---------------------------------------------------------------------------------------
+def keccak256(data: bytes) -> bytes:
+    """Keccak-256 (the pre-NIST padding Ethereum uses); host-only glue, not on the GPU path."""
+    rc = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
+          0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
+          0x0000000080008009, 0x000000008000000A, 0x000000008000808B, 0x800000000000008B, 0x8000000000008089,
+          0x8000000000008003, 0x8000000000008002, 0x8000000000000080, 0x000000000000800A, 0x800000008000000A,
+          0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]
+    rot = [[0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14]]
+    m64 = (1 << 64) - 1
+
+    def rol(x, n):
+        return ((x << n) | (x >> (64 - n))) & m64 if n else x
+    rate = 136
+    p = bytearray(data)
+    p.append(0x01)
+    while len(p) % rate:
+        p.append(0)
+    p[-1] |= 0x80
+    a = [[0] * 5 for _ in range(5)]
+    for off in range(0, len(p), rate):
+        for i in range(rate // 8):
+            a[i % 5][i // 5] ^= int.from_bytes(p[off + 8 * i:off + 8 * i + 8], "little")
+        for rnd in range(24):
+            c = [a[x][0] ^ a[x][1] ^ a[x][2] ^ a[x][3] ^ a[x][4] for x in range(5)]
+            d = [c[(x - 1) % 5] ^ rol(c[(x + 1) % 5], 1) for x in range(5)]
+            a = [[a[x][y] ^ d[x] for y in range(5)] for x in range(5)]
+            b = [[0] * 5 for _ in range(5)]
+            for x in range(5):
+                for y in range(5):
+                    b[y][(2 * x + 3 * y) % 5] = rol(a[x][y], rot[x][y])
+            a = [[b[x][y] ^ ((~b[(x + 1) % 5][y]) & b[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+            a[0][0] ^= rc[rnd]
+    return b"".join(a[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
+
+
+def instance_hash(chain_id: int, verifier_address: bytes, transition: Sequence[bytes], sgx_instance: bytes, prover: bytes,
+                  meta_hash: bytes, proof_of_equivalence: Tuple[int, int] = (0, 0),
+                  proof_of_equivalence_feature: bool = True) -> bytes:
+    """protocol_instance.rs:165-185: keccak256 of abi.encode("VERIFY_PROOF", chainId, verifier,
+    transition{parentHash, blockHash, stateRoot, graffiti}, newInstance, prover, metaHash
+    [, proof_of_equivalence]) with the outer offset word skipped."""
+    def word(v: int) -> bytes:
+        return int(v).to_bytes(32, "big")
+
+    def addr(a: bytes) -> bytes:
+        if len(a) != 20:
+            raise ValueError("address must be 20 bytes")
+        return bytes(12) + bytes(a)
+    if len(transition) != 4 or any(len(t) != 32 for t in transition) or len(meta_hash) != 32:
+        raise ValueError("transition is 4 x bytes32, meta_hash bytes32")
+    static = [word(chain_id), addr(verifier_address)] + [bytes(t) for t in transition] + [addr(sgx_instance), addr(prover), bytes(meta_hash)]
+    if proof_of_equivalence_feature:
+        static += [word(proof_of_equivalence[0]), word(proof_of_equivalence[1])]
+    tag = b"VERIFY_PROOF"
+    head_len = 32 * (1 + len(static))
+    data = word(head_len) + b"".join(static) + word(len(tag)) + tag + bytes(32 - len(tag))
+    return keccak256(data)
+
+
+# ---------------------------------------------------------------------------------------
 # blob -> tx-list codec (lib/src/utils.rs:85-144)
 # ---------------------------------------------------------------------------------------
 BLOB_DATA_STRIDE = 130048

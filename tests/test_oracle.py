@@ -154,3 +154,24 @@ def test_call_site_host_logic():
         callers.calc_blob_versioned_hash("0x00")          # wrong length: "Could not create blob"
     with pytest.raises(LookupError):
         callers.find_tx_blob([], bytes(32))
+
+
+def test_instance_hash_reference_kat():
+    """lib/src/protocol_instance.rs:241-276 (test_calc_eip712_pi_hash): the public-input hash that
+    proof_of_equivalence feeds, reproduced by raiko_b200/callers.py."""
+    from raiko_b200 import callers
+    assert callers.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    trans = [bytes.fromhex(h) for h in (
+        "07828133348460fab349c7e0e9fd8e08555cba34b34f215ffc846bfbce0e8f52",
+        "e2105909de032b913abfa4c8b6101f9863d82be109ef32890b771ae214784efa",
+        "abbd12b3bcb836b024c413bb8c9f58f5bb626d6d835f5554a8240933e40b2d3b",
+        "00" * 32)]
+    h = callers.instance_hash(167001, bytes.fromhex("4F3F0D5B22338f1f991a1a9686C7171389C97Ff7"), trans,
+                              bytes.fromhex("741E45D08C70c1C232802711bBFe1B7C0E1acc55"),
+                              bytes.fromhex("70997970C51812dc3A010C7d01b50e0d17dc79C8"),
+                              bytes.fromhex("9608088f69e586867154a693565b4f3234f26f82d44ef43fb99fd774e7266024"), (0, 0))
+    assert h.hex() == "dc1696a5289616fa5eaa9b6ce97d53765b79db948caedb6887f21a26e4c29511"
+    # the (x, y) words change the hash; without the feature the tuple is two words shorter
+    assert callers.instance_hash(167001, bytes(20), trans, bytes(20), bytes(20), bytes(32), (1, 2)) != \\
+        callers.instance_hash(167001, bytes(20), trans, bytes(20), bytes(20), bytes(32), (2, 1))
+    assert len(callers.instance_hash(1, bytes(20), trans, bytes(20), bytes(20), bytes(32), proof_of_equivalence_feature=False)) == 32
