@@ -172,6 +172,6 @@ def test_instance_hash_reference_kat():
                               bytes.fromhex("9608088f69e586867154a693565b4f3234f26f82d44ef43fb99fd774e7266024"), (0, 0))
     assert h.hex() == "dc1696a5289616fa5eaa9b6ce97d53765b79db948caedb6887f21a26e4c29511"
     # the (x, y) words change the hash; without the feature the tuple is two words shorter
-    assert callers.instance_hash(167001, bytes(20), trans, bytes(20), bytes(20), bytes(32), (1, 2)) != \\
+    assert callers.instance_hash(167001, bytes(20), trans, bytes(20), bytes(20), bytes(32), (1, 2)) != \
         callers.instance_hash(167001, bytes(20), trans, bytes(20), bytes(20), bytes(32), (2, 1))
     assert len(callers.instance_hash(1, bytes(20), trans, bytes(20), bytes(20), bytes(32), proof_of_equivalence_feature=False)) == 32
