@@ -262,6 +262,32 @@ RK_HD void line_coeffs(LineCoeffs& l, const Fp2& lam, const Fp2& xt, const Fp2& 
     l.l3 = yp;
 }
 
+// Invert NP Fp2 denominators with one Fp2 inversion (Montgomery's trick); entries of dead
+// pairs are skipped.  A zero denominator cannot occur for points of prime order r.
+template <int NP>
+RK_HD void fp2_batch_inv(Fp2* den, const bool* live) {
+    Fp2 pre[NP], run;
+    bool any = false;
+    for (int k = 0; k < NP; k++) {
+        if (!live[k]) continue;
+        if (!any) { run = den[k]; any = true; pre[k] = den[k]; }     // pre[k] unused for the first live entry
+        else { pre[k] = run; fp2_mul(run, run, den[k]); }
+    }
+    if (!any) return;
+    Fp2 inv;
+    fp2_inv(inv, run);
+    int first = -1;
+    for (int k = 0; k < NP; k++) if (live[k]) { first = k; break; }
+    for (int k = NP - 1; k > first; k--) {
+        if (!live[k]) continue;
+        Fp2 t;
+        fp2_mul(t, inv, pre[k]);          // 1 / den[k]
+        fp2_mul(inv, inv, den[k]);
+        den[k] = t;
+    }
+    den[first] = inv;
+}
+
 template <int NP>
 RK_HD_NOINLINE void miller_loop(Fp12& f, const G1Affine* ps, const int* p_inf, const G2Affine* qs) {
     fp12_one(f);
@@ -271,15 +297,18 @@ RK_HD_NOINLINE void miller_loop(Fp12& f, const G1Affine* ps, const int* p_inf, c
     const uint64_t e = ((uint64_t)BLS_X_ABS_W32::at(1) << 32) | BLS_X_ABS_W32::at(0);
     for (int bit = 62; bit >= 0; bit--) {
         fp12_sqr(f, f);
+        Fp2 num[NP], den[NP];
+        for (int k = 0; k < NP; k++) {            // tangent slopes 3x^2 / 2y, denominators inverted together
+            if (!live[k]) continue;
+            fp2_sqr(num[k], t[k].x);
+            fp2_add(den[k], num[k], num[k]); fp2_add(num[k], den[k], num[k]);
+            fp2_add(den[k], t[k].y, t[k].y);
+        }
+        fp2_batch_inv<NP>(den, live);
         for (int k = 0; k < NP; k++) {
             if (!live[k]) continue;
-            // tangent at T
-            Fp2 lam, num, den, x3, y3;
-            fp2_sqr(num, t[k].x);
-            fp2_add(den, num, num); fp2_add(num, den, num);        // 3 x^2
-            fp2_add(den, t[k].y, t[k].y);
-            fp2_inv(den, den);
-            fp2_mul(lam, num, den);
+            Fp2 lam, x3, y3;
+            fp2_mul(lam, num[k], den[k]);
             LineCoeffs l;
             line_coeffs(l, lam, t[k].x, t[k].y, ps[k].x, ps[k].y);
             fp12_mul_line(f, f, l);
@@ -288,13 +317,16 @@ RK_HD_NOINLINE void miller_loop(Fp12& f, const G1Affine* ps, const int* p_inf, c
             t[k].x = x3; t[k].y = y3;
         }
         if ((e >> bit) & 1) {
+            for (int k = 0; k < NP; k++) {        // chord slopes (yQ - yT) / (xQ - xT)
+                if (!live[k]) continue;
+                fp2_sub(num[k], qs[k].y, t[k].y);
+                fp2_sub(den[k], qs[k].x, t[k].x);
+            }
+            fp2_batch_inv<NP>(den, live);
             for (int k = 0; k < NP; k++) {
                 if (!live[k]) continue;
-                Fp2 lam, num, den, x3, y3;
-                fp2_sub(num, qs[k].y, t[k].y);
-                fp2_sub(den, qs[k].x, t[k].x);
-                fp2_inv(den, den);
-                fp2_mul(lam, num, den);
+                Fp2 lam, x3, y3;
+                fp2_mul(lam, num[k], den[k]);
                 LineCoeffs l;
                 line_coeffs(l, lam, t[k].x, t[k].y, ps[k].x, ps[k].y);
                 fp12_mul_line(f, f, l);
