@@ -646,12 +646,29 @@ rk_status verify_core(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, int n, const u
     // [s]G2 then the generator
     CUDA_TRY(cudaMemcpyAsync(d_g2, ctx->g2_be.data() + 192, 192, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_g2 + 192, ctx->g2_be.data(), 192, cudaMemcpyHostToDevice, st));
+    // RAIKO_KZG_VERIFY_TRACE=1 prints the per-stage device time of this call to stderr
+    const bool trace = getenv("RAIKO_KZG_VERIFY_TRACE") != nullptr;
+    cudaEvent_t ev[7];
+    if (trace) for (auto& e : ev) cudaEventCreate(&e);
+    auto mark = [&](int i) { if (trace) cudaEventRecord(ev[i], st); };
+    mark(0);
     k_g1_decompress_validate<<<(n + 63) / 64, 64, 0, st>>>(d_c, n, d_pts, d_inf, d_flags + 0);
     k_g1_decompress_validate<<<(n + 63) / 64, 64, 0, st>>>(d_p, n, d_pts + n, d_inf + n, d_flags + 1);
+    mark(1);
     k_batch_challenge<<<1, 1, 0, st>>>(d_c, d_z, d_y, d_p, n, d_r);
+    mark(2);
     k_verify_terms<<<(n + 63) / 64, 64, 0, st>>>(d_r, d_z, d_y, d_pts, d_inf, d_pts + n, d_inf + n, n, d_a, d_e, d_t, d_flags + 2);
+    mark(3);
     k_verify_reduce<<<1, VR_THREADS, 0, st>>>(d_a, d_e, d_t, n, d_pair, d_pinf);
+    mark(4);
     k_pairing_check<<<1, 1, 0, st>>>(d_pair, d_pinf, d_g2, d_g2 + 192, d_flags + 3);
+    mark(5);
+    if (trace) {
+        cudaEventSynchronize(ev[5]);
+        const char* names[5] = {"decompress+subgroup", "batch challenge", "r-power terms", "reduce", "pairing"};
+        for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, "[verify n=%d] %-20s %8.3f ms\n", n, names[i], ms); }
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     d->stats.total_launches += 6;
     CUDA_TRY(cudaGetLastError());
     int flags[4];

@@ -920,40 +920,37 @@ __device__ __forceinline__ bool fr_words_from_be_canon(uint32_t (&s)[8], const u
 }
 
 // r = hash_to_bls_field(sha256("RCKZGBATCH___V1_" | be64(4096) | be64(n) | (C_i | z_i | y_i | proof_i)*)), one thread.
+// The transcript is a sequence of 16-byte-aligned fields, so it is fed word-wise (uint4 loads);
+// the chain itself is serial by construction.
 __global__ void k_batch_challenge(const uint8_t* c, const uint8_t* z, const uint8_t* y, const uint8_t* pr, int n, Fr* out_r) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Sha256State st;
     sha256_init(st);
-    uint8_t buf[64];
-    int fill = 0;
-    uint64_t total = 0;
-    auto push = [&](const uint8_t* p, int len) {
-        for (int i = 0; i < len; i++) {
-            buf[fill++] = p[i];
-            if (fill == 64) {
-                uint32_t w[16];
-                for (int k = 0; k < 16; k++) w[k] = load_be32(buf + 4 * k);
-                sha256_compress(st, w);
-                fill = 0;
-            }
-        }
-        total += (uint64_t)len;
+    uint32_t w[16];
+    int fill = 0;                                   // words in w
+    auto push_word = [&](uint32_t v) {
+        w[fill++] = v;
+        if (fill == 16) { sha256_compress(st, w); fill = 0; }
     };
-    const uint8_t dom[16] = {'R', 'C', 'K', 'Z', 'G', 'B', 'A', 'T', 'C', 'H', '_', '_', '_', 'V', '1', '_'};
-    uint8_t hdr[16] = {0, 0, 0, 0, 0, 0, 0x10, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = 0; k < 8; k++) hdr[8 + k] = (uint8_t)((uint64_t)n >> (56 - 8 * k));
-    push(dom, 16);
-    push(hdr, 16);
+    auto push16 = [&](const uint8_t* p, int quads) {    // quads x 16 bytes, 16-byte aligned
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        for (int i = 0; i < quads; i++) {
+            uint4 v = q[i];
+            push_word(__byte_perm(v.x, 0, 0x0123)); push_word(__byte_perm(v.y, 0, 0x0123));
+            push_word(__byte_perm(v.z, 0, 0x0123)); push_word(__byte_perm(v.w, 0, 0x0123));
+        }
+    };
+    // "RCKZGBATCH___V1_" | be64(4096) | be64(n)
+    push_word(0x52434b5au); push_word(0x47424154u); push_word(0x43485f5fu); push_word(0x5f56315fu);
+    push_word(0); push_word(4096u); push_word(0); push_word((uint32_t)n);
     for (int i = 0; i < n; i++) {
-        push(c + 48 * (size_t)i, 48); push(z + 32 * (size_t)i, 32); push(y + 32 * (size_t)i, 32); push(pr + 48 * (size_t)i, 48);
+        push16(c + 48 * (size_t)i, 3); push16(z + 32 * (size_t)i, 2); push16(y + 32 * (size_t)i, 2); push16(pr + 48 * (size_t)i, 3);
     }
-    const uint64_t bits = total * 8;
-    uint8_t one = 0x80, zero = 0;
-    push(&one, 1);
-    while (fill != 56) push(&zero, 1);
-    uint8_t len[8];
-    for (int k = 0; k < 8; k++) len[k] = (uint8_t)(bits >> (56 - 8 * k));
-    push(len, 8);
+    const uint64_t bits = (32ull + 160ull * (uint64_t)n) * 8ull;
+    push_word(0x80000000u);
+    while (fill != 14) push_word(0);
+    push_word((uint32_t)(bits >> 32));
+    push_word((uint32_t)bits);
     uint8_t h[32];
     for (int i = 0; i < 8; i++) store_be32(h + 4 * i, st.h[i]);
     Fr rm, rc;

@@ -137,7 +137,22 @@ RK_HD_NOINLINE void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
         }
     fp12_fold(r, t);
 }
-RK_HD void fp12_sqr(Fp12& r, const Fp12& a) { fp12_mul(r, a, a); }
+// square: 78 products instead of 144 (cross terms once, doubled)
+RK_HD_NOINLINE void fp12_sqr(Fp12& r, const Fp12& a) {
+    Fp t[23];
+    for (int k = 0; k < 23; k++) fe_zero(t[k]);
+    for (int i = 0; i < 12; i++) {
+        Fp m;
+        fe_sqr(m, a.c[i]);
+        fq_add(t[2 * i], t[2 * i], m);
+        for (int j = i + 1; j < 12; j++) {
+            fe_mul(m, a.c[i], a.c[j]);
+            fq_dbl(m, m);
+            fq_add(t[i + j], t[i + j], m);
+        }
+    }
+    fp12_fold(r, t);
+}
 // a * (l0 + l6 w^6 + l2 w^2 + l8 w^8 + l3 w^3): the shape of a line function
 struct LineCoeffs { Fp l0, l6, l2, l8, l3; };
 RK_HD_NOINLINE void fp12_mul_line(Fp12& r, const Fp12& a, const LineCoeffs& l) {
