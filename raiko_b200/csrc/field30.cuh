@@ -23,10 +23,10 @@
 
 #ifdef __CUDACC__
 #define RK_HD __host__ __device__ __forceinline__
-#define RK_HD_NOINLINE __host__ __device__ __noinline__
+#define RK_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define RK_HD inline
-#define RK_HD_NOINLINE
+#define RK_HD_NOINLINE static
 #endif
 
 #define RK_CONST_ARRAY(T, NAME, N, ...)                                  \

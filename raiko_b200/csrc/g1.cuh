@@ -65,8 +65,8 @@ RK_HD void g1_dbl(G1Xyzz& r, const G1Xyzz& a) {
 // is ~15 KB.  The CUDA ABI keeps both 13-word operands and the result in registers (checked:
 // no local-memory traffic, tools/ubench/noinline_test.cu), and the call costs ~3 %.
 #ifdef __CUDACC__
-__device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) { Fp r; fe_mul(r, a, b); return r; }
-__device__ __noinline__ Fp fp_sqr_call(Fp a) { Fp r; fe_sqr(r, a); return r; }
+static __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) { Fp r; fe_mul(r, a, b); return r; }
+static __device__ __noinline__ Fp fp_sqr_call(Fp a) { Fp r; fe_sqr(r, a); return r; }
 #endif
 template <bool CALLS>
 RK_HD void fp_mul_sel(Fp& r, const Fp& a, const Fp& b) {

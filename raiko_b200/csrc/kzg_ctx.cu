@@ -18,7 +18,7 @@
 #include <vector>
 
 #include "../../include/raiko_kzg.h"
-#include "kzg_kernels.cuh"
+#include "kzg_launch.h"
 
 using namespace rk;
 
@@ -103,9 +103,6 @@ struct DeviceCtx {
     ChunkSlot slot[2];
     std::mutex mu;
     int sm_count = 148;
-    // MSM kernel variant (RAIKO_KZG_MSM_REGS, experiments only): 255 = inlined + CTA-lockstep barrier
-    // (default, fastest), 254 = no barrier, 253 = out-of-line multiplies, 128 = 16 warps/SM at 128 registers
-    int msm_variant = 255;
     int warps_per_sm = 8;
     // Blob hashing runs on the main stream ahead of the commitment MSM.  Beside it (own stream,
     // RAIKO_KZG_SHA_SERIAL=0) its latency-bound warps sit in the MSM's issue slots and cost the
@@ -230,8 +227,8 @@ rk_status load_setup(DeviceCtx* d, const uint8_t* data, size_t len, std::vector<
     const size_t g1_bytes = ref_format ? 144ull * NPTS : 48ull * NPTS;
     CUDA_TRY(cudaMalloc(&d_in, g1_bytes));
     CUDA_TRY(cudaMemcpy(d_in, data + g1_off, g1_bytes, cudaMemcpyHostToDevice));
-    if (ref_format) k_setup_from_ref<<<NPTS / 64, 64>>>(d_in, NPTS, d->g1_aff, d_err);
-    else k_setup_decompress<<<NPTS / 64, 64>>>(d_in, NPTS, d->g1_aff, d_err);
+    if (ref_format) launch_k_setup_from_ref(NPTS / 64, 64, 0, 0, d_in, NPTS, d->g1_aff, d_err);
+    else launch_k_setup_decompress(NPTS / 64, 64, 0, 0, d_in, NPTS, d->g1_aff, d_err);
     CUDA_TRY(cudaGetLastError());
     int err = 0;
     CUDA_TRY(cudaMemcpy(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost));
@@ -248,7 +245,7 @@ rk_status load_setup(DeviceCtx* d, const uint8_t* data, size_t len, std::vector<
             CUDA_TRY(cudaMalloc(&d_g2, 288 * N_G2));
             CUDA_TRY(cudaMalloc(&d_o, 288 * N_G2));
             CUDA_TRY(cudaMemcpy(d_g2, data + g2_off, 288 * N_G2, cudaMemcpyHostToDevice));
-            k_fp_ref_to_be<<<(6 * N_G2 + 63) / 64, 64>>>(d_g2, 6 * N_G2, d_o);
+            launch_k_fp_ref_to_be((6 * N_G2 + 63) / 64, 64, 0, 0, d_g2, 6 * N_G2, d_o);
             std::vector<uint8_t> tmp(288 * N_G2);
             CUDA_TRY(cudaMemcpy(tmp.data(), d_o, tmp.size(), cudaMemcpyDeviceToHost));
             cudaFree(d_g2); cudaFree(d_o);
@@ -277,17 +274,17 @@ rk_status build_table(DeviceCtx* d) {
     CUDA_TRY(cudaMalloc(&bases, sizeof(G1Xyzz) * chains));
     CUDA_TRY(cudaMalloc(&bases_aff, sizeof(G1Affine) * chains));
     CUDA_TRY(cudaMalloc(&state, sizeof(G1Xyzz) * chains));
-    k_table_bases<<<NPTS / 64, 64>>>(d->g1_aff, g, bases);
-    k_table_bases_affine<<<(chains / 16 + 63) / 64, 64>>>(bases, chains, bases_aff);
+    launch_k_table_bases(NPTS / 64, 64, 0, 0, d->g1_aff, g, bases);
+    launch_k_table_bases_affine((chains / 16 + 63) / 64, 64, 0, 0, bases, chains, bases_aff);
     CUDA_TRY(cudaGetLastError());
     const uint32_t emax = std::max(g.half, g.top_entries);
     int D = 256;
     while ((uint32_t)D > emax && D > TABLE_NORM_G) D >>= 1;
     CUDA_TRY(cudaMalloc(&tmp, sizeof(G1Xyzz) * (size_t)chains * D));
     for (uint32_t d0 = 1; d0 <= emax; d0 += D) {
-        k_table_chain<<<(chains + 127) / 128, 128>>>(bases_aff, g, d0, D, state, tmp);
+        launch_k_table_chain((chains + 127) / 128, 128, 0, 0, bases_aff, g, d0, D, state, tmp);
         const long long groups = (long long)chains * (D / TABLE_NORM_G);
-        k_table_normalize<<<(unsigned)((groups + 127) / 128), 128>>>(g, d0, D, tmp, d->table);
+        launch_k_table_normalize((unsigned)((groups + 127) / 128), 128, 0, 0, g, d0, D, tmp, d->table);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
@@ -329,9 +326,8 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, d->dev));
     d->sm_count = prop.multiProcessorCount;
-    if (const char* e = getenv("RAIKO_KZG_MSM_REGS")) d->msm_variant = atoi(e);
     if (const char* e = getenv("RAIKO_KZG_SHA_SERIAL")) d->sha_serial = atoi(e) != 0;
-    d->warps_per_sm = d->msm_variant == 128 ? 16 : 8;
+    d->warps_per_sm = 8;                   // k_msm: 256-thread CTAs at 248 registers
     if (prop.major < 10)
         return fail(RK_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", d->dev, prop.major, prop.minor);
     int c = window_bits;
@@ -356,11 +352,10 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
     CUDA_TRY(cudaStreamCreateWithFlags(&d->s_sha, cudaStreamDefault));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->s_in, cudaStreamDefault));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->s_out, cudaStreamDefault));
-    CUDA_TRY(cudaFuncSetAttribute(k_fr_eval_quot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM_BYTES));
     rk_status st = load_setup(d, settings, len, g2_be);
     if (st != RK_OK) return st;
     CUDA_TRY(cudaMalloc(&d->roots, sizeof(Fr) * NPTS));
-    k_roots_brp<<<NPTS / 128, 128>>>(d->roots);
+    launch_k_roots_brp(NPTS / 128, 128, 0, 0, d->roots);
     CUDA_TRY(cudaGetLastError());
     st = build_table(d);
     if (st != RK_OK) return st;
@@ -410,10 +405,7 @@ void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint3
     p.partials = s.d_partials; p.bad = bad;
     const long long warps = (long long)n << p.splits_log2;
     timer_begin(d, d->s_main, T_MSM);
-    if (d->msm_variant == 128) k_msm_r128<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
-    else if (d->msm_variant == 253) k_msm_calls<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
-    else if (d->msm_variant == 254) k_msm_nosync<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
-    else k_msm<<<(unsigned)((warps + 7) / 8), 256, 0, d->s_main>>>(p);
+    launch_k_msm((unsigned)((warps + 7) / 8), 256, 0, d->s_main, p);
     timer_end(d, d->s_main);
     d->stats.msm_point_adds += (uint64_t)n * NPTS * d->geom.W;
     *splits_out = 1 << p.splits_log2;
@@ -487,8 +479,8 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             timer_begin(d, hs, T_SHA);
             // <= 8 blobs (a Cancun block has <= 6): the MSM leaves SMs free, use the two-warp hash.
             // Larger batches keep the one-warp kernel, whose 2048 registers fit beside an MSM CTA.
-            if (cnt <= 8) k_sha_blob_duo<<<cnt, 64, 0, hs>>>(d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
-            else k_sha_blob<<<(cnt + 31) / 32, 32, 0, hs>>>(d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
+            if (cnt <= 8) launch_k_sha_blob_duo(cnt, 64, 0, hs, d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
+            else launch_k_sha_blob((cnt + 31) / 32, 32, 0, hs, d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
             timer_end(d, hs);
             CUDA_TRY(cudaEventRecord(s.ev_sha, hs));
         }
@@ -497,8 +489,8 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
         if (a.mode == MODE_COMMIT || a.mode == MODE_COMMIT_PROVE) {
             launch_msm(d, d_blobs, cnt, s, s.d_bad, &splits);
             timer_begin(d, d->s_main, T_FIN);
-            if (splits >= 8) k_finalize_warp<<<cnt, 32, 0, d->s_main>>>(s.d_partials, splits, cnt, s.d_bad, o + OFF_C, o + OFF_VH, o_stat, OUT_STRIDE);
-            else k_finalize<<<(cnt + 31) / 32, 32, 0, d->s_main>>>(s.d_partials, splits, cnt, s.d_bad, o + OFF_C, o + OFF_VH,
+            if (splits >= 8) launch_k_finalize_warp(cnt, 32, 0, d->s_main, s.d_partials, splits, cnt, s.d_bad, o + OFF_C, o + OFF_VH, o_stat, OUT_STRIDE);
+            else launch_k_finalize((cnt + 31) / 32, 32, 0, d->s_main, s.d_partials, splits, cnt, s.d_bad, o + OFF_C, o + OFF_VH,
                                                               o_stat, OUT_STRIDE);
             timer_end(d, d->s_main);
         }
@@ -515,19 +507,19 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             fp.out_stride = OUT_STRIDE;
             fp.inv_scratch = s.d_inv;
             timer_begin(d, d->s_main, T_FR);
-            k_fr_eval_quot<<<cnt, FR_THREADS, FR_SMEM_BYTES, d->s_main>>>(fp);
+            launch_k_fr_eval_quot(cnt, FR_THREADS, FR_SMEM_BYTES, d->s_main, fp);
             timer_end(d, d->s_main);
             if (fp.want_quotient) {
                 launch_msm(d, s.d_q, cnt, s, nullptr, &splits);
                 timer_begin(d, d->s_main, T_FIN);
-                if (splits >= 8) k_finalize_warp<<<cnt, 32, 0, d->s_main>>>(s.d_partials, splits, cnt, s.d_bad, o + OFF_PROOF, nullptr, o_stat, OUT_STRIDE);
-                else k_finalize<<<(cnt + 31) / 32, 32, 0, d->s_main>>>(s.d_partials, splits, cnt, s.d_bad, o + OFF_PROOF, nullptr,
+                if (splits >= 8) launch_k_finalize_warp(cnt, 32, 0, d->s_main, s.d_partials, splits, cnt, s.d_bad, o + OFF_PROOF, nullptr, o_stat, OUT_STRIDE);
+                else launch_k_finalize((cnt + 31) / 32, 32, 0, d->s_main, s.d_partials, splits, cnt, s.d_bad, o + OFF_PROOF, nullptr,
                                                                   o_stat, OUT_STRIDE);
                 timer_end(d, d->s_main);
-                k_status_only<<<(cnt + 127) / 128, 128, 0, d->s_main>>>(s.d_bad, cnt, o, o_stat, OUT_STRIDE, OFF_HASH);
+                launch_k_status_only((cnt + 127) / 128, 128, 0, d->s_main, s.d_bad, cnt, o, o_stat, OUT_STRIDE, OFF_HASH);
                 d->stats.total_launches++;
             } else {
-                k_status_only<<<(cnt + 127) / 128, 128, 0, d->s_main>>>(s.d_bad, cnt, o, o_stat, OUT_STRIDE, OFF_HASH);
+                launch_k_status_only((cnt + 127) / 128, 128, 0, d->s_main, s.d_bad, cnt, o, o_stat, OUT_STRIDE, OFF_HASH);
                 d->stats.total_launches++;
             }
         }
@@ -652,16 +644,16 @@ rk_status verify_core(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, int n, const u
     if (trace) for (auto& e : ev) cudaEventCreate(&e);
     auto mark = [&](int i) { if (trace) cudaEventRecord(ev[i], st); };
     mark(0);
-    k_g1_decompress_validate<<<(n + 63) / 64, 64, 0, st>>>(d_c, n, d_pts, d_inf, d_flags + 0);
-    k_g1_decompress_validate<<<(n + 63) / 64, 64, 0, st>>>(d_p, n, d_pts + n, d_inf + n, d_flags + 1);
+    launch_k_g1_decompress_validate((n + 63) / 64, 64, 0, st, d_c, n, d_pts, d_inf, d_flags + 0);
+    launch_k_g1_decompress_validate((n + 63) / 64, 64, 0, st, d_p, n, d_pts + n, d_inf + n, d_flags + 1);
     mark(1);
-    k_batch_challenge<<<1, 1, 0, st>>>(d_c, d_z, d_y, d_p, n, d_r);
+    launch_k_batch_challenge(1, 1, 0, st, d_c, d_z, d_y, d_p, n, d_r);
     mark(2);
-    k_verify_terms<<<(n + 63) / 64, 64, 0, st>>>(d_r, d_z, d_y, d_pts, d_inf, d_pts + n, d_inf + n, n, d_a, d_e, d_t, d_flags + 2);
+    launch_k_verify_terms((n + 63) / 64, 64, 0, st, d_r, d_z, d_y, d_pts, d_inf, d_pts + n, d_inf + n, n, d_a, d_e, d_t, d_flags + 2);
     mark(3);
-    k_verify_reduce<<<1, VR_THREADS, 0, st>>>(d_a, d_e, d_t, n, d_pair, d_pinf);
+    launch_k_verify_reduce(1, VR_THREADS, 0, st, d_a, d_e, d_t, n, d_pair, d_pinf);
     mark(4);
-    k_pairing_check<<<1, 1, 0, st>>>(d_pair, d_pinf, d_g2, d_g2 + 192, d_flags + 3);
+    launch_k_pairing_check(1, 1, 0, st, d_pair, d_pinf, d_g2, d_g2 + 192, d_flags + 3);
     mark(5);
     if (trace) {
         cudaEventSynchronize(ev[5]);
@@ -714,14 +706,14 @@ rk_status verify_blob_batch_device(rk_kzg_ctx* ctx, const uint8_t* blobs, const 
             d_blobs = s.d_blobs;
         }
         timer_begin(d, st, T_SHA);
-        k_sha_fs_challenge<<<(cnt + 31) / 32, 32, 0, st>>>(d_blobs, d_c + 48 * first, cnt, d_z + 32 * first);
+        launch_k_sha_fs_challenge((cnt + 31) / 32, 32, 0, st, d_blobs, d_c + 48 * first, cnt, d_z + 32 * first);
         timer_end(d, st);
         FrParams fp{};
         fp.blobs = d_blobs; fp.roots_brp = d->roots; fp.z_in = d_z + 32 * first; fp.mode = 1; fp.want_quotient = 0; fp.eval = 1;
         fp.nblobs = cnt; fp.out_stride = 32; fp.out_x = nullptr; fp.out_y = d_y + 32 * first; fp.q_out = nullptr; fp.bad = d_bad + first;
         fp.inv_scratch = s.d_inv;
         timer_begin(d, st, T_FR);
-        k_fr_eval_quot<<<cnt, FR_THREADS, FR_SMEM_BYTES, st>>>(fp);
+        launch_k_fr_eval_quot(cnt, FR_THREADS, FR_SMEM_BYTES, st, fp);
         timer_end(d, st);
         CUDA_TRY(cudaEventRecord(s.ev_done, st));
     }
@@ -827,7 +819,7 @@ rk_status rk_kzg_ctx_export_settings(rk_kzg_ctx* ctx, int kind, uint8_t* out, si
     const size_t g1b = 144ull * NPTS, g2b = 288ull * N_G2, rb = 32ull * 4097;
     CUDA_TRY(cudaMalloc(&d_buf, g1b + g2b + 3 * rb + 192 * N_G2));
     uint8_t *d_g1 = d_buf, *d_g2 = d_buf + g1b, *d_r0 = d_g2 + g2b, *d_r1 = d_r0 + rb, *d_r2 = d_r1 + rb, *d_g2in = d_r2 + rb;
-    k_setup_to_ref<<<NPTS / 64, 64>>>(d->g1_aff, NPTS, d_g1);
+    launch_k_setup_to_ref(NPTS / 64, 64, 0, 0, d->g1_aff, NPTS, d_g1);
     // G2: x.c0 x.c1 y.c0 y.c1 (BE) -> 6 Montgomery coordinates with Z = (1, 0)
     std::vector<uint8_t> g2six(288 * N_G2, 0);
     for (int i = 0; i < N_G2; i++) {
@@ -837,10 +829,10 @@ rk_status rk_kzg_ctx_export_settings(rk_kzg_ctx* ctx, int kind, uint8_t* out, si
     uint8_t* d_g2be = nullptr;
     CUDA_TRY(cudaMalloc(&d_g2be, g2six.size()));
     CUDA_TRY(cudaMemcpy(d_g2be, g2six.data(), g2six.size(), cudaMemcpyHostToDevice));
-    k_fp_be_to_ref<<<(6 * N_G2 + 63) / 64, 64>>>(d_g2be, 6 * N_G2, d_g2);
-    k_roots_export<<<(4097 + 63) / 64, 64>>>(0, 4097, d_r0);
-    k_roots_export<<<(4097 + 63) / 64, 64>>>(1, 4097, d_r1);
-    k_roots_export<<<(4096 + 63) / 64, 64>>>(2, 4096, d_r2);
+    launch_k_fp_be_to_ref((6 * N_G2 + 63) / 64, 64, 0, 0, d_g2be, 6 * N_G2, d_g2);
+    launch_k_roots_export((4097 + 63) / 64, 64, 0, 0, 0, 4097, d_r0);
+    launch_k_roots_export((4097 + 63) / 64, 64, 0, 0, 1, 4097, d_r1);
+    launch_k_roots_export((4096 + 63) / 64, 64, 0, 0, 2, 4096, d_r2);
     (void)d_g2in;
     CUDA_TRY(cudaGetLastError());
     std::vector<uint8_t> h(g1b + g2b + 3 * rb);
@@ -1110,7 +1102,7 @@ rk_status rk_decode_blob_data_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_
         }
         uint8_t* d_o = out_dev ? out + first * BLOBDATA_STRIDE : s.d_q;          // d_q: chunk * 131072 >= chunk * stride
         uint32_t* d_l = out_dev ? out_len + first : d_len;
-        k_decode_blob_data<<<cnt, 256, 0, st>>>(d_blobs, cnt, d_o, d_l);
+        launch_k_decode_blob_data(cnt, 256, 0, st, d_blobs, cnt, d_o, d_l);
         d->stats.total_launches++;
         CUDA_TRY(cudaGetLastError());
         if (!out_dev) {
@@ -1159,7 +1151,7 @@ rk_status rk_measure_imad_peak(int device, double* out_macs_per_sec, double* out
     float best = 1e30f;
     for (int rep = 0; rep < 6; rep++) {
         cudaEventRecord(e0);
-        k_imad_peak<<<blocks, 256>>>(d_out, 3, iters);
+        launch_k_imad_peak(blocks, 256, 0, 0, d_out, 3, iters);
         cudaEventRecord(e1);
         CUDA_TRY(cudaEventSynchronize(e1));
         float ms = 0;

@@ -16,6 +16,8 @@
 namespace rk {
 
 constexpr int NPTS = 4096;             // FIELD_ELEMENTS_PER_BLOB
+constexpr int TABLE_NORM_G = 32;       // multiples normalised per thread in k_table_normalize
+constexpr int VR_THREADS = 128;        // k_verify_reduce block size
 constexpr int BLOB_BYTES = 131072;
 
 // ---------------------------------------------------------------------------
@@ -84,6 +86,7 @@ __device__ __forceinline__ void load_scalar_be(uint32_t (&s)[8], const uint8_t* 
     s[1] = __byte_perm(lo.z, 0, 0x0123); s[0] = __byte_perm(lo.w, 0, 0x0123);
 }
 
+#ifdef RK_TU_MSM
 template <int THREADS, int MIN_BLOCKS, int SYNC_EVERY, bool CALLS>
 __device__ __forceinline__ void msm_body(const MsmParams& prm) {
     const int lane = threadIdx.x & 31;
@@ -178,17 +181,12 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
 }
 
 
-// Variants of the same body kept for A/B measurements (RAIKO_KZG_MSM_REGS): measured on B200,
-// 8 warps/SM x 248 registers with the lockstep barrier is the fastest (2.35 G additions/s);
-// 12 warps x 168 registers 2.2-2.3, 16 warps x 128 registers 2.2, no barrier 1.94,
-// out-of-line multiplies 1.92 (profiles/r01/).
-// 248 registers (not 255): 8 warps then leave 2048 registers per SM, enough for one k_sha_blob
-// warp to be co-resident instead of taking an SM of its own.
+// 8 warps/SM x 248 registers with the lockstep barrier is the fastest configuration measured on
+// B200 (2.35 G additions/s); 12 warps x 168 registers 2.2-2.3, 16 warps x 128 registers 2.2,
+// no barrier 1.94, out-of-line multiplies 1.92 (profiles/r01/).  248 registers (not 255): 8 warps
+// then leave 2048 registers per SM, enough for one k_sha_blob warp to be co-resident.
 __global__ void __maxnreg__(248) k_msm(MsmParams prm) { msm_body<256, 1, 1, false>(prm); }
-__global__ void __launch_bounds__(256, 1) k_msm_calls(MsmParams prm) { msm_body<256, 1, 0, true>(prm); }
-__global__ void __launch_bounds__(256, 1) k_msm_nosync(MsmParams prm) { msm_body<256, 1, 0, false>(prm); }
-
-__global__ void __launch_bounds__(256, 2) k_msm_r128(MsmParams prm) { msm_body<256, 2, 0, true>(prm); }
+#endif  // RK_TU_MSM
 
 // ---------------------------------------------------------------------------
 // k_finalize: one thread per blob.  Sums the blob's partial sums, converts to affine
@@ -197,6 +195,7 @@ __global__ void __launch_bounds__(256, 2) k_msm_r128(MsmParams prm) { msm_body<2
 // A blob flagged `bad` (non-canonical field element; Eip4844Error::DeserializeBlob)
 // gets zeroed outputs and status RK_ERR_NONCANONICAL_FE (= 2).
 // ---------------------------------------------------------------------------
+#ifdef RK_TU_PATH
 __global__ void __launch_bounds__(32) k_finalize(const G1Xyzz* partials, int splits, int nblobs,
                                                   const uint32_t* bad, uint8_t* out_g1,
                                                   uint8_t* out_vh, uint8_t* status, int stride) {
@@ -358,6 +357,7 @@ __global__ void __launch_bounds__(64) k_sha_blob_duo(const uint8_t* blobs, int n
     }
 }
 
+#endif  // RK_TU_PATH
 // ---------------------------------------------------------------------------
 // k_fr_eval_quot: one CTA (256 threads) per blob, 16 field elements per thread.
 //
@@ -419,6 +419,7 @@ __device__ __forceinline__ void fr_from_be_reduce(Fr& mont, Fr& canon, const uin
 constexpr int FR_THREADS = 256;
 constexpr int FR_PER_THREAD = NPTS / FR_THREADS;   // 16
 
+#ifdef RK_TU_PATH
 __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // per-element prefix products / inverses live in global scratch (coalesced: thread t touches
@@ -607,11 +608,13 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
         }
     }
 }
+#endif  // RK_TU_PATH
 constexpr size_t FR_SMEM_BYTES = sizeof(Fr) * (FR_THREADS + 32 + 4);
 
 // ---------------------------------------------------------------------------
 // Trusted-setup decoding
 // ---------------------------------------------------------------------------
+#ifdef RK_TU_TABLE
 // compressed 48-byte points -> affine Montgomery.  err[0] = first failing index + 1.
 __global__ void k_setup_decompress(const uint8_t* in, int n, G1Affine* out, int* err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -800,7 +803,6 @@ __global__ void __launch_bounds__(128) k_table_chain(const G1Affine* bases_aff, 
     state[chain] = acc;
 }
 // Stage B2: normalise tmp into table entries; thread per (chain, group of G multiples).
-constexpr int TABLE_NORM_G = 32;
 __global__ void __launch_bounds__(128) k_table_normalize(TableGeom g, uint32_t d0, int D, const G1Xyzz* tmp,
                                                          TableEntry* table) {
     const int groups_per_chain = D / TABLE_NORM_G;
@@ -817,9 +819,11 @@ __global__ void __launch_bounds__(128) k_table_normalize(TableGeom g, uint32_t d
     normalize_run<TABLE_NORM_G>(tmp + (size_t)chain * D + (size_t)grp * TABLE_NORM_G, count, nullptr, dst);
 }
 
+#endif  // RK_TU_TABLE
 // ---------------------------------------------------------------------------
 // Integer-multiply peak (roofline denominator): independent mad.wide.u32 chains.
 // ---------------------------------------------------------------------------
+#ifdef RK_TU_PATH
 __global__ void __launch_bounds__(256) k_imad_peak(uint64_t* out, uint32_t seed, int iters) {
     uint64_t w[8];
     uint32_t b = seed | 1u, c = threadIdx.x * 2654435761u + 12345u;
@@ -838,12 +842,14 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint64_t* out, uint32_t seed,
     out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = r;
 }
 
+#endif  // RK_TU_PATH
 }  // namespace rk
 
 // ===========================================================================
 // Verification (BASELINE.json configs[4]):
 // verify_kzg_proof and verify_blob_kzg_proof_batch (Deneb spec, App. B.6).
 // ===========================================================================
+#ifdef RK_TU_VERIFY
 #include "pairing.cuh"
 
 namespace rk {
@@ -993,7 +999,6 @@ __global__ void __launch_bounds__(64) k_verify_terms(const Fr* r_mont, const uin
 
 // One CTA: PL = sum A_i, ER = sum E_i - (sum t_i) * G; writes the two pairing inputs
 // (-PL, ER) as affine points with infinity flags.
-constexpr int VR_THREADS = 128;
 __global__ void __launch_bounds__(VR_THREADS) k_verify_reduce(const G1Xyzz* a, const G1Xyzz* e, const Fr* t, int n, G1Affine* out_pts, int* out_inf) {
     __shared__ G1Xyzz sh[VR_THREADS];
     __shared__ Fr sht[VR_THREADS];
@@ -1043,6 +1048,12 @@ __global__ void __launch_bounds__(VR_THREADS) k_verify_reduce(const G1Xyzz* a, c
     }
 }
 
+}  // namespace rk
+#endif  // RK_TU_VERIFY
+
+#ifdef RK_TU_PAIRING
+#include "pairing.cuh"
+namespace rk {
 // e(pts[0], [s]G2) * e(pts[1], G2) == 1 ?   Single thread.
 __global__ void k_pairing_check(const G1Affine* pts, const int* inf, const uint8_t* g2_s_be, const uint8_t* g2_gen_be, int* out_ok) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -1055,6 +1066,7 @@ __global__ void k_pairing_check(const G1Affine* pts, const int* inf, const uint8
 }
 
 }  // namespace rk
+#endif  // RK_TU_PAIRING
 
 // ===========================================================================
 // Blob -> tx-list byte codec (lib/src/utils.rs:80-179, decode_blob_data; SURVEY.md §8(f)
@@ -1068,6 +1080,7 @@ namespace rk {
 constexpr int BLOBDATA_MAX = (4 * 31 + 3) * 1024 - 4;      // 130 044
 constexpr int BLOBDATA_STRIDE = 130048;                     // output bytes reserved per blob
 
+#ifdef RK_TU_PATH
 __global__ void __launch_bounds__(256) k_decode_blob_data(const uint8_t* blobs, int nblobs, uint8_t* out, uint32_t* out_len) {
     const int blob = blockIdx.x;
     const int tid = threadIdx.x;
@@ -1120,4 +1133,5 @@ __global__ void __launch_bounds__(256) k_decode_blob_data(const uint8_t* blobs, 
     if (tid == 0) out_len[blob] = s_bad ? 0u : (uint32_t)len;
 }
 
+#endif  // RK_TU_PATH
 }  // namespace rk

@@ -49,7 +49,7 @@ struct Fp2 { Fp c0, c1; };
 RK_HD void fp2_add(Fp2& r, const Fp2& a, const Fp2& b) { fq_add(r.c0, a.c0, b.c0); fq_add(r.c1, a.c1, b.c1); }
 RK_HD void fp2_sub(Fp2& r, const Fp2& a, const Fp2& b) { fq_sub(r.c0, a.c0, b.c0); fq_sub(r.c1, a.c1, b.c1); }
 RK_HD void fp2_neg(Fp2& r, const Fp2& a) { fq_neg(r.c0, a.c0); fq_neg(r.c1, a.c1); }
-RK_HD void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
+RK_HD_NOINLINE void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
     Fp v0, v1, s, t, u;
     fe_mul(v0, a.c0, b.c0);
     fe_mul(v1, a.c1, b.c1);
@@ -60,7 +60,7 @@ RK_HD void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
     fq_sub(r.c1, u, v1);
     fq_sub(r.c0, v0, v1);
 }
-RK_HD void fp2_sqr(Fp2& r, const Fp2& a) {
+RK_HD_NOINLINE void fp2_sqr(Fp2& r, const Fp2& a) {
     Fp s, d, m;
     fq_add(s, a.c0, a.c1);
     fq_sub(d, a.c0, a.c1);
@@ -68,8 +68,8 @@ RK_HD void fp2_sqr(Fp2& r, const Fp2& a) {
     fe_mul(r.c0, s, d);
     fq_add(r.c1, m, m);
 }
-RK_HD void fp2_mul_fp(Fp2& r, const Fp2& a, const Fp& k) { fe_mul(r.c0, a.c0, k); fe_mul(r.c1, a.c1, k); }
-RK_HD void fp2_inv(Fp2& r, const Fp2& a) {
+RK_HD_NOINLINE void fp2_mul_fp(Fp2& r, const Fp2& a, const Fp& k) { fe_mul(r.c0, a.c0, k); fe_mul(r.c1, a.c1, k); }
+RK_HD_NOINLINE void fp2_inv(Fp2& r, const Fp2& a) {
     Fp n0, n1, n, ninv;
     fe_sqr(n0, a.c0);
     fe_sqr(n1, a.c1);
@@ -175,12 +175,14 @@ RK_HD void fp12_conj(Fp12& r, const Fp12& a) {      // Frobenius^6: w -> -w
 }
 // Frobenius p^k (k = 1, 2) through the constant table FP12_FROBk
 template <class TAB>
+RK_HD_NOINLINE uint32_t frob_word(int i) { return TAB::at(i); }     // one copy of the 312-word table per TAB
+template <class TAB>
 RK_HD_NOINLINE void fp12_frob(Fp12& r, const Fp12& a) {
     Fp t[12];
     for (int k = 0; k < 12; k++) fe_zero(t[k]);
     for (int j = 0; j < 12; j++) {
         Fp lo, hi, m;
-        for (int l = 0; l < FP_N; l++) { lo.v[l] = TAB::at(j * 26 + l); hi.v[l] = TAB::at(j * 26 + 13 + l); }
+        for (int l = 0; l < FP_N; l++) { lo.v[l] = frob_word<TAB>(j * 26 + l); hi.v[l] = frob_word<TAB>(j * 26 + 13 + l); }
         fe_mul(m, a.c[j], lo); fq_add(t[j % 6], t[j % 6], m);
         fe_mul(m, a.c[j], hi); fq_add(t[j % 6 + 6], t[j % 6 + 6], m);
     }
@@ -266,7 +268,7 @@ RK_HD_NOINLINE bool final_exp_is_one(const Fp12& f) {
 // ---------------------------------------------------------------------------
 // Miller loop for up to NP pairs, product of f_{|x|,Q_k}(P_k)
 // ---------------------------------------------------------------------------
-RK_HD void line_coeffs(LineCoeffs& l, const Fp2& lam, const Fp2& xt, const Fp2& yt, const Fp& xp, const Fp& yp) {
+RK_HD_NOINLINE void line_coeffs(LineCoeffs& l, const Fp2& lam, const Fp2& xt, const Fp2& yt, const Fp& xp, const Fp& yp) {
     Fp2 c0, c2;
     fp2_mul(c0, lam, xt);
     fp2_sub(c0, c0, yt);                       // lam*xT - yT
