@@ -24,6 +24,7 @@ extern "C" {
     pub fn rk_commit_prove_batch(ctx: *mut rk_kzg_ctx, blobs: *const u8, n: usize, out_c: *mut u8, out_vh: *mut u8, out_x: *mut u8, out_y: *mut u8, out_proofs: *mut u8, status: *mut u8) -> rk_status;
     pub fn rk_compute_kzg_proof_batch(ctx: *mut rk_kzg_ctx, blobs: *const u8, zs: *const u8, n: usize, out_proofs: *mut u8, out_y: *mut u8, status: *mut u8) -> rk_status;
     pub fn rk_verify_kzg_proof(ctx: *mut rk_kzg_ctx, commitment: *const u8, z: *const u8, y: *const u8, proof: *const u8, out_ok: *mut c_int) -> rk_status;
+    pub fn rk_verify_kzg_proof_batch(ctx: *mut rk_kzg_ctx, commitments: *const u8, zs: *const u8, ys: *const u8, proofs: *const u8, n: usize, out_ok: *mut c_int) -> rk_status;
     pub fn rk_verify_blob_kzg_proof_batch(ctx: *mut rk_kzg_ctx, blobs: *const u8, commitments: *const u8, proofs: *const u8, n: usize, out_ok: *mut c_int) -> rk_status;
     pub fn rk_decode_blob_data_batch(ctx: *mut rk_kzg_ctx, blobs: *const u8, n: usize, out: *mut u8, out_len: *mut u32) -> rk_status;
     pub fn rk_last_error() -> *const c_char;

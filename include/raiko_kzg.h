@@ -121,6 +121,13 @@ rk_status rk_compute_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, cons
  * RK_ERR_NONCANONICAL_FE, like upstream's Err results.                                        */
 rk_status rk_verify_kzg_proof(rk_kzg_ctx* ctx, const uint8_t commitment[48], const uint8_t z[32],
                               const uint8_t y[32], const uint8_t proof[48], int* out_ok);
+/* verify_kzg_proof_batch (Deneb spec; the routine upstream's verify_blob_kzg_proof_batch ends in):
+ * n tuples (C_i, z_i, y_i, proof_i) checked with ONE random-linear-combination transcript and two
+ * pairings per <= 16384 tuples.  Inputs host or device.  This is also the whole-batch self-check of
+ * rk_commit_prove_batch (z = x: every (C, x, y, proof) of a 65,536-blob batch in under a second). */
+rk_status rk_verify_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* commitments /* n*48 */,
+                                    const uint8_t* zs /* n*32 */, const uint8_t* ys /* n*32 */,
+                                    const uint8_t* proofs /* n*48 */, size_t n, int* out_ok);
 /* verify_blob_kzg_proof_batch (Deneb spec): per blob the EIP-4844 Fiat-Shamir challenge
  * (NOT raiko's evaluation point), y = p(z), then one random-linear-combination check with two
  * pairings, all on ctx device 0.  blobs may be host or device memory; commitments / proofs

@@ -39,6 +39,7 @@ SIGNATURES = {
     "rk_compute_kzg_proof_batch": (_I, [_P, _P, _P, _SZ, _P, _P, _P]),
     "rk_verify_kzg_proof": (_I, [_P, _P, _P, _P, _P, ctypes.POINTER(_I)]),
     "rk_verify_blob_kzg_proof_batch": (_I, [_P, _P, _P, _P, _SZ, ctypes.POINTER(_I)]),
+    "rk_verify_kzg_proof_batch": (_I, [_P, _P, _P, _P, _P, _SZ, ctypes.POINTER(_I)]),
     "rk_decode_blob_data_batch": (_I, [_P, _P, _SZ, _P, _P]),
     "rk_kzg_stats_enable": (None, [_P, _I]),
     "rk_kzg_stats_reset": (None, [_P]),

@@ -1054,6 +1054,37 @@ rk_status rk_verify_kzg_proof(rk_kzg_ctx* ctx, const uint8_t commitment[48], con
     return verify_core(ctx, d, buf, 1, d_in, d_in + 48, d_in + 96, d_in + 128, out_ok);
 }
 
+rk_status rk_verify_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* commitments, const uint8_t* zs, const uint8_t* ys,
+                                    const uint8_t* proofs, size_t n, int* out_ok) {
+    if (!ctx || !out_ok) return fail(RK_ERR_ARG, "null argument");
+    *out_ok = 0;
+    if (n == 0) { *out_ok = 1; return RK_OK; }
+    if (!commitments || !zs || !ys || !proofs) return fail(RK_ERR_ARG, "null argument");
+    DeviceCtx* d = ctx->devs[0];
+    std::lock_guard<std::mutex> lock(d->mu);
+    CUDA_TRY(cudaSetDevice(d->dev));
+    // one random-linear-combination transcript (and one two-pairing check) per <= 16384 tuples
+    int all = 1;
+    for (size_t first = 0; first < n; first += VERIFY_MAX_N) {
+        const size_t cnt = std::min(VERIFY_MAX_N, n - first);
+        DevBuf buf;
+        uint8_t *d_c = nullptr, *d_p = nullptr, *d_z = nullptr, *d_y = nullptr;
+        CUDA_TRY(buf.alloc(&d_c, 48 * cnt)); CUDA_TRY(buf.alloc(&d_p, 48 * cnt));
+        CUDA_TRY(buf.alloc(&d_z, 32 * cnt)); CUDA_TRY(buf.alloc(&d_y, 32 * cnt));
+        cudaStream_t st = d->s_main;
+        CUDA_TRY(cudaMemcpyAsync(d_c, commitments + 48 * first, 48 * cnt, cudaMemcpyDefault, st));
+        CUDA_TRY(cudaMemcpyAsync(d_p, proofs + 48 * first, 48 * cnt, cudaMemcpyDefault, st));
+        CUDA_TRY(cudaMemcpyAsync(d_z, zs + 32 * first, 32 * cnt, cudaMemcpyDefault, st));
+        CUDA_TRY(cudaMemcpyAsync(d_y, ys + 32 * first, 32 * cnt, cudaMemcpyDefault, st));
+        int ok = 0;
+        rk_status rc = verify_core(ctx, d, buf, (int)cnt, d_c, d_p, d_z, d_y, &ok);
+        if (rc != RK_OK) return rc;
+        all &= ok;
+    }
+    *out_ok = all;
+    return RK_OK;
+}
+
 rk_status rk_verify_blob_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments,
                                          const uint8_t* proofs, size_t n, int* out_ok) {
     if (!ctx || !out_ok) return fail(RK_ERR_ARG, "null argument");

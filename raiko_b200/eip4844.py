@@ -20,7 +20,7 @@ __all__ = [
     "ComputeKzgProof", "KzgSettings", "KZGSettings", "kzg_settings", "set_kzg_settings", "get_evaluation_point",
     "proof_of_equivalence", "calc_kzg_proof", "calc_kzg_proof_with_point", "calc_kzg_proof_commitment",
     "commitment_to_version_hash", "kzg_proof_to_bytes", "blob_to_kzg_commitment", "compute_kzg_proof",
-    "kzg_to_versioned_hash", "verify_kzg_proof", "verify_blob_kzg_proof_batch", "commit_batch", "commit_prove_batch", "compute_kzg_proof_batch", "BatchResult",
+    "kzg_to_versioned_hash", "verify_kzg_proof", "verify_kzg_proof_batch", "verify_blob_kzg_proof_batch", "commit_batch", "commit_prove_batch", "compute_kzg_proof_batch", "BatchResult",
     "DEFAULT_SETTINGS_PATH",
 ]
 
@@ -278,6 +278,23 @@ def verify_kzg_proof(commitment: bytes, z: bytes, y: bytes, proof: bytes, settin
     ok = ctypes.c_int(0)
     _check(s._lib.rk_verify_kzg_proof(s._ctx, _cptr(bytes(commitment)), _cptr(bytes(z)), _cptr(bytes(y)), _cptr(bytes(proof)),
                                       ctypes.byref(ok)))
+    return bool(ok.value)
+
+
+def verify_kzg_proof_batch(commitments, zs, ys, proofs, settings: Optional[KzgSettings] = None) -> bool:
+    """verify_kzg_proof_batch (Deneb spec): n (C, z, y, proof) tuples under one random linear
+    combination and two pairings.  Each argument is a sequence of byte strings, one contiguous
+    bytes-like object, or a CUDA tensor (device pointers go straight through the C ABI)."""
+    s = _s(settings)
+
+    def flat(v):
+        return _Buf(b"".join(bytes(e) for e in v) if isinstance(v, (list, tuple)) else v)
+    c, z, y, p = flat(commitments), flat(zs), flat(ys), flat(proofs)
+    n = c.nbytes // 48
+    if (c.nbytes, z.nbytes, y.nbytes, p.nbytes) != (48 * n, 32 * n, 32 * n, 48 * n):
+        raise ValueError("need n x (commitment48, z32, y32, proof48)")
+    ok = ctypes.c_int(0)
+    _check(s._lib.rk_verify_kzg_proof_batch(s._ctx, c.ptr, z.ptr, y.ptr, p.ptr, n, ctypes.byref(ok)))
     return bool(ok.value)
 
 

@@ -76,3 +76,97 @@ def test_verify_blob_kzg_proof_batch(gpu_settings, pyoracle):
     bad = b"\xff" * 32 + blobs[0][32:]
     with pytest.raises(rk.DeserializeBlob):
         rk.verify_blob_kzg_proof_batch([bad], commitments[:1], proofs[:1], gpu_settings)
+
+
+def _golden_tuples(golden):
+    out = []
+    for case in golden["cases"]:
+        for p in case["proofs"]:
+            out.append((bytes.fromhex(case["commitment"]), bytes.fromhex(p["z"]), bytes.fromhex(p["y"]), bytes.fromhex(p["proof"])))
+    return out
+
+
+def test_verify_kzg_proof_batch_goldens(gpu_settings, golden):
+    """verify_kzg_proof_batch: every pairing-validated golden tuple under ONE random linear
+    combination; any single altered field of any tuple must flip the verdict."""
+    import raiko_b200 as rk
+    t = _golden_tuples(golden)
+    cs, zs, ys, ps = (list(col) for col in zip(*t))
+    assert len(t) >= 8
+    assert rk.verify_kzg_proof_batch(cs, zs, ys, ps, gpu_settings)
+    assert rk.verify_kzg_proof_batch([], [], [], [], gpu_settings)          # vacuous
+    assert rk.verify_kzg_proof_batch(cs[:1], zs[:1], ys[:1], ps[:1], gpu_settings)
+    k = len(t) - 2
+    y1 = ((int.from_bytes(ys[k], "big") + 1) % R).to_bytes(32, "big")
+    assert not rk.verify_kzg_proof_batch(cs, zs, ys[:k] + [y1] + ys[k + 1:], ps, gpu_settings)
+    z1 = ((int.from_bytes(zs[1], "big") + 1) % R).to_bytes(32, "big")
+    assert not rk.verify_kzg_proof_batch(cs, [zs[0], z1] + zs[2:], ys, ps, gpu_settings)
+    # a proof that is a valid G1 point but belongs to another tuple
+    j = next(i for i in range(1, len(t)) if ps[i] != ps[0])
+    assert not rk.verify_kzg_proof_batch(cs, zs, ys, [ps[j]] + ps[1:], gpu_settings)
+    with pytest.raises(rk.DeserializeBlob):
+        rk.verify_kzg_proof_batch(cs, [b"\xff" * 32] + zs[1:], ys, ps, gpu_settings)
+    with pytest.raises(ValueError):
+        rk.verify_kzg_proof_batch([bytes([cs[0][0] & 0x7F]) + cs[0][1:]] + cs[1:], zs, ys, ps, gpu_settings)
+
+
+def test_full_size_65536_blob_batch_self_check(ref):
+    """BASELINE.json configs[3] at full size.  The oracle cannot redo 131 072 MSMs in a test, so the
+    65,536-blob commit+prove batch is pinned through size-independent properties:
+      * status 0 everywhere, versioned hash = 0x01 | sha256(C)[1:] for every blob (hashlib);
+      * (x, y) of EVERY blob equal the C oracle's proof_of_equivalence (challenge + barycentric
+        evaluation: ~1 ms per blob on the host, all cores);
+      * every (C, x, y, proof) passes the pairing check under a random linear combination
+        (rk_verify_kzg_proof_batch).  With y = p(x) established independently at the
+        Fiat-Shamir point x = H(blob, C), an accepting proof forces C = commit(p)
+        (Schwartz-Zippel), and proofs are unique given (C, x, y): commitments and proofs are
+        bit-exact without recomputing a single MSM on the CPU;
+      * C, proof of a spread sample equal the C oracle byte for byte anyway;
+      * altering one byte of one y makes the batch check fail."""
+    import hashlib
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    import torch
+    import raiko_b200 as rk
+    from raiko_b200 import _native
+    n = int(os.environ.get("RAIKO_KZG_FULL_BATCH", "65536"))
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(65536)
+    blobs = torch.empty((n, 4096, 32), dtype=torch.uint8, device=dev)
+    for i in range(0, n, 4096):
+        j = min(n, i + 4096)
+        blobs[i:j] = torch.randint(0, 256, (j - i, 4096, 32), dtype=torch.uint8, device=dev, generator=gen)
+    blobs[:, :, 0] %= 0x73
+    s = rk.KzgSettings(devices=[0], window_bits=int(os.environ.get("RAIKO_KZG_FULL_WINDOW_BITS", "0")))
+    try:
+        lib = _native.load()
+        outs = {k: torch.zeros((n, w), dtype=torch.uint8, device=dev)
+                for k, w in (("c", 48), ("vh", 32), ("x", 32), ("y", 32), ("p", 48), ("st", 1))}
+        st = lib.rk_commit_prove_batch(s._ctx, blobs.data_ptr(), n, outs["c"].data_ptr(), outs["vh"].data_ptr(),
+                                       outs["x"].data_ptr(), outs["y"].data_ptr(), outs["p"].data_ptr(), outs["st"].data_ptr())
+        assert st == 0, _native.last_error()
+        assert int(outs["st"].sum()) == 0
+        h = {k: v.cpu().numpy() for k, v in outs.items()}
+        for i in range(n):
+            c = h["c"][i].tobytes()
+            assert h["vh"][i].tobytes() == b"\x01" + hashlib.sha256(c).digest()[1:]
+
+        host_blobs = blobs.cpu().numpy()
+
+        def xy(i):
+            return ref.proof_of_equivalence(host_blobs[i].tobytes(), h["vh"][i].tobytes())
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+            want = list(ex.map(xy, range(n)))
+        for i in range(n):
+            assert (h["x"][i].tobytes(), h["y"][i].tobytes()) == want[i], i
+
+        assert rk.verify_kzg_proof_batch(outs["c"], outs["x"], outs["y"], outs["p"], s)
+        for i in (0, n // 2 + 1, n - 1):                                         # byte-level spot check
+            got = tuple(h[k][i].tobytes() for k in ("c", "vh", "x", "y", "p"))
+            assert got == ref.commit_prove(host_blobs[i].tobytes())
+        bad = outs["y"].clone()
+        bad[n // 3, 31] ^= 1
+        assert not rk.verify_kzg_proof_batch(outs["c"], outs["x"], bad, outs["p"], s)
+    finally:
+        s.close()
