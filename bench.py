@@ -178,7 +178,7 @@ def run_reference(args):
     import kzg_ref
     kzg_ref.build()
     cores = os.cpu_count() or 1
-    per_step = max(cores, 16)
+    per_step = max(4 * cores, 64)      # ~1 s of work per host thread per step: thread start-up does not dominate
     arr = synth_blobs_host(per_step, seed=20241018)
     blobs = [arr[i].tobytes() for i in range(per_step)]
     for _ in range(args.warmup):

@@ -99,8 +99,11 @@ def test_verify_kzg_proof_batch_goldens(gpu_settings, golden):
     k = len(t) - 2
     y1 = ((int.from_bytes(ys[k], "big") + 1) % R).to_bytes(32, "big")
     assert not rk.verify_kzg_proof_batch(cs, zs, ys[:k] + [y1] + ys[k + 1:], ps, gpu_settings)
-    z1 = ((int.from_bytes(zs[1], "big") + 1) % R).to_bytes(32, "big")
-    assert not rk.verify_kzg_proof_batch(cs, [zs[0], z1] + zs[2:], ys, ps, gpu_settings)
+    # z only matters where the proof is not the point at infinity (constant polynomials: q = 0)
+    inf = b"\xc0" + bytes(47)
+    m = next(i for i in range(len(t)) if ps[i] != inf)
+    z1 = ((int.from_bytes(zs[m], "big") + 1) % R).to_bytes(32, "big")
+    assert not rk.verify_kzg_proof_batch(cs, zs[:m] + [z1] + zs[m + 1:], ys, ps, gpu_settings)
     # a proof that is a valid G1 point but belongs to another tuple
     j = next(i for i in range(1, len(t)) if ps[i] != ps[0])
     assert not rk.verify_kzg_proof_batch(cs, zs, ys, [ps[j]] + ps[1:], gpu_settings)
