@@ -282,6 +282,22 @@ RK_HD void fe_cond_sub_mod(Fe<F>& a) {
     }
 }
 
+// Loose reduction of any normalised value (< 2^(30 N)): subtracts q * mod with the quotient
+// estimated from the top limb, q = top / (mod_top + 1) <= a / mod.  Result in
+// [0, mod * (1 + (q + 2) / mod_top)), i.e. below 1.0001 mod for the fields here.
+template <class F>
+RK_HD void fe_reduce_loose(Fe<F>& a) {
+    constexpr int N = F::N;
+    const uint32_t q = a.v[N - 1] / (F::MOD::at(N - 1) + 1u);
+    int64_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        int64_t t = (int64_t)a.v[i] - (int64_t)((uint64_t)q * F::MOD::at(i)) + carry;
+        if (i < N - 1) { a.v[i] = launder((uint32_t)t & LIMB_MASK); carry = t >> LIMB_BITS; }
+        else a.v[i] = (uint32_t)t;
+    }
+}
+
 // Montgomery -> canonical integer in [0, mod)
 template <class F>
 RK_HD void fe_from_mont(Fe<F>& r, const Fe<F>& a) {
@@ -349,6 +365,102 @@ RK_HD_NOINLINE void fe_pow_const(Fe<F>& r, const Fe<F>& a) {
 template <class F>
 RK_HD void fe_inv(Fe<F>& r, const Fe<F>& a) {
     fe_pow_const<F, typename F::EXP_INV, F::W32>(r, a);
+}
+
+// ---------------------------------------------------------------------------
+// Inversion by Bernstein-Yang division steps ("safegcd", half-delta variant), 30 steps
+// per outer iteration on the low limbs, the accumulated 2x2 transition matrix then applied
+// to the full-width (f, g) and to (d, e) modulo the field -- the same signed-30-bit-limb
+// shape as this file's products, so every product is again a carry-less IMAD.WIDE.
+// 26-27 outer iterations for a 381-bit modulus (20 for 255 bits): ~35 Fp-mul equivalents,
+// against ~440 for the Fermat ladder above.  That order of magnitude is what makes batched
+// AFFINE point addition (g1.cuh: one shared inversion per few dozen additions) cheaper than
+// inversion-free XYZZ addition in the MSM hot loop.
+//
+// Input: Montgomery form, < 8 mod, normalised limbs, != 0 mod p.  Output: Montgomery form of
+// the inverse, fully reduced to [0, mod).  (d, e) start as (0, R^2), so the Montgomery
+// factors cancel: (aR)^-1 * R^2 = a^-1 R.  Zero returns 0; other multiples of the modulus have no
+// inverse and return an unspecified value (callers exclude them).
+// ---------------------------------------------------------------------------
+template <class F>
+RK_HD void fe_inv_safegcd(Fe<F>& out, const Fe<F>& a) {
+    constexpr int N = F::N;
+    constexpr int32_t M30 = (int32_t)LIMB_MASK;
+    int32_t d[N], e[N], f[N], g[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { d[i] = 0; e[i] = (int32_t)F::R2::at(i); f[i] = (int32_t)F::MOD::at(i); g[i] = (int32_t)a.v[i]; }
+    int32_t zeta = -1;                              // -(delta + 1/2)
+    for (int it = 0; it < 4 * N; it++) {            // proven bound for these sizes is below 37; the loop ends on g == 0
+        uint32_t nz = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) nz |= (uint32_t)g[i];
+        if (nz == 0) break;
+        // ---- 30 division steps on the low words; (u v; q r) accumulates the transition matrix
+        uint32_t u = 1, v = 0, q = 0, r = 1, fl = (uint32_t)f[0] | ((uint32_t)f[1] << 30), gl = (uint32_t)g[0] | ((uint32_t)g[1] << 30);
+#pragma unroll 6
+        for (int s = 0; s < 30; s++) {
+            uint32_t m1 = (uint32_t)(zeta >> 31), m2 = 0u - (gl & 1u);
+            uint32_t x = (fl ^ m1) - m1, y = (u ^ m1) - m1, z = (v ^ m1) - m1;
+            gl += x & m2; q += y & m2; r += z & m2;
+            m1 &= m2;
+            zeta = (int32_t)((uint32_t)zeta ^ m1) - 1;
+            fl += gl & m1; u += q & m1; v += r & m1;
+            gl >>= 1; u <<= 1; v <<= 1;
+        }
+        const int32_t U = (int32_t)u, V = (int32_t)v, Q = (int32_t)q, Rr = (int32_t)r;
+        // ---- (d, e) <- (U d + V e, Q d + R e) / 2^30  modulo the field
+        {
+            const int32_t sd = d[N - 1] >> 31, se = e[N - 1] >> 31;
+            int32_t md = (U & sd) + (V & se), me = (Q & sd) + (Rr & se);
+            int64_t cd = (int64_t)U * d[0] + (int64_t)V * e[0];
+            int64_t ce = (int64_t)Q * d[0] + (int64_t)Rr * e[0];
+            md -= (int32_t)((F::MINV * (uint32_t)cd + (uint32_t)md) & LIMB_MASK);
+            me -= (int32_t)((F::MINV * (uint32_t)ce + (uint32_t)me) & LIMB_MASK);
+            cd += (int64_t)(int32_t)F::MOD::at(0) * md;
+            ce += (int64_t)(int32_t)F::MOD::at(0) * me;
+            cd >>= 30; ce >>= 30;
+#pragma unroll
+            for (int i = 1; i < N; i++) {
+                cd += (int64_t)U * d[i] + (int64_t)V * e[i] + (int64_t)(int32_t)F::MOD::at(i) * md;
+                ce += (int64_t)Q * d[i] + (int64_t)Rr * e[i] + (int64_t)(int32_t)F::MOD::at(i) * me;
+                d[i - 1] = (int32_t)cd & M30; cd >>= 30;
+                e[i - 1] = (int32_t)ce & M30; ce >>= 30;
+            }
+            d[N - 1] = (int32_t)cd; e[N - 1] = (int32_t)ce;
+        }
+        // ---- (f, g) <- (U f + V g, Q f + R g) / 2^30  (exact)
+        {
+            int64_t cf = (int64_t)U * f[0] + (int64_t)V * g[0];
+            int64_t cg = (int64_t)Q * f[0] + (int64_t)Rr * g[0];
+            cf >>= 30; cg >>= 30;
+#pragma unroll
+            for (int i = 1; i < N; i++) {
+                cf += (int64_t)U * f[i] + (int64_t)V * g[i];
+                cg += (int64_t)Q * f[i] + (int64_t)Rr * g[i];
+                f[i - 1] = (int32_t)cf & M30; cf >>= 30;
+                g[i - 1] = (int32_t)cg & M30; cg >>= 30;
+            }
+            f[N - 1] = (int32_t)cf; g[N - 1] = (int32_t)cg;
+        }
+    }
+    // f = +-1 now; result = sign(f) * d, brought from (-2 mod, mod) into [0, mod)
+    const int32_t neg = f[N - 1] >> 31;
+    int32_t add = d[N - 1] >> 31, carry = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        int32_t t = d[i] + ((int32_t)F::MOD::at(i) & add);
+        t = (t ^ neg) - neg;
+        t += carry;
+        if (i < N - 1) { carry = t >> 30; t &= M30; }
+        d[i] = t;
+    }
+    add = d[N - 1] >> 31; carry = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        int32_t t = d[i] + ((int32_t)F::MOD::at(i) & add) + carry;
+        if (i < N - 1) { carry = t >> 30; t &= M30; }
+        out.v[i] = (uint32_t)t;
+    }
 }
 
 }  // namespace rk

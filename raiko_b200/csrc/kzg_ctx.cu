@@ -108,6 +108,14 @@ struct DeviceCtx {
     // RAIKO_KZG_SHA_SERIAL=0) its latency-bound warps sit in the MSM's issue slots and cost the
     // MSM 3-6 %, more than the 3.3 ms per chunk the hash takes alone.
     bool sha_serial = true;
+    // MSM formulation: 1 = batched affine additions (k_msm_affine) for launches whose lanes own
+    // enough table entries to fill the chains, 0 = XYZZ only (k_msm).  RAIKO_KZG_MSM_AFFINE.
+    int msm_affine = 1;
+    int aff_chains = MSM_AFF_MAX_K;
+    int aff_min_entries = 8 * MSM_AFF_MAX_K;   // per-lane table entries below which k_msm is used
+    int max_splits_log2 = 7;                   // test knob: 0 forces one warp per blob
+    uint32_t* aff_scratch = nullptr;       // sm_count x chains x 39 words x 256 threads
+    uint32_t recode_h[8] = {0};
     // stats
     bool stats_on = false;
     std::vector<KernelTimer> timers;
@@ -188,7 +196,7 @@ void free_device(DeviceCtx* d) {
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         if (s.ev_out) cudaEventDestroy(s.ev_out);
     }
-    cudaFree(d->table); cudaFree(d->roots); cudaFree(d->g1_aff);
+    cudaFree(d->table); cudaFree(d->roots); cudaFree(d->g1_aff); cudaFree(d->aff_scratch);
     if (d->s_main) cudaStreamDestroy(d->s_main);
     if (d->s_sha) cudaStreamDestroy(d->s_sha);
     if (d->s_in) cudaStreamDestroy(d->s_in);
@@ -304,6 +312,21 @@ rk_status alloc_slots(DeviceCtx* d) {
         if (v >= 1 && v <= 16384) d->chunk = v;
     }
     d->max_partials = std::max(16 * d->chunk, 128 * 128);
+    if (const char* e = getenv("RAIKO_KZG_MSM_AFFINE")) d->msm_affine = atoi(e);
+    if (const char* e = getenv("RAIKO_KZG_AFFINE_CHAINS")) d->aff_chains = std::min(MSM_AFF_MAX_K, std::max(1, atoi(e)));
+    d->aff_min_entries = 8 * d->aff_chains;
+    if (const char* e = getenv("RAIKO_KZG_AFFINE_MIN_ENTRIES")) d->aff_min_entries = std::max(1, atoi(e));
+    if (const char* e = getenv("RAIKO_KZG_MAX_SPLITS_LOG2")) d->max_splits_log2 = std::min(7, std::max(0, atoi(e)));
+    if (d->msm_affine) {
+        CUDA_TRY(configure_k_msm_affine());
+        CUDA_TRY(cudaMalloc(&d->aff_scratch, (size_t)d->sm_count * d->aff_chains * AFF_WORDS * 256 * sizeof(uint32_t)));
+        // H = sum_{j < W-1} 2^(c-1) * 2^(cj): adding it turns unsigned digits into signed ones
+        memset(d->recode_h, 0, sizeof d->recode_h);
+        for (int j = 0; j < d->geom.W - 1; j++) {
+            const int bit = d->geom.c * j + d->geom.c - 1;
+            if (bit < 256) d->recode_h[bit >> 5] |= 1u << (bit & 31);
+        }
+    }
     for (auto& s : d->slot) {
         CUDA_TRY(cudaMalloc(&s.d_q, (size_t)d->chunk * BLOB_BYTES));
         CUDA_TRY(cudaMalloc(&s.d_partials, sizeof(G1Xyzz) * (size_t)d->max_partials));
@@ -388,7 +411,7 @@ int pick_splits_log2(const DeviceCtx* d, size_t nblobs) {
     const double adds_per_lane = (double)NPTS * d->geom.W / 32.0;
     int best = 0;
     double best_t = 1e300;
-    for (int lg = 0; lg <= 7; lg++) {
+    for (int lg = 0; lg <= d->max_splits_log2; lg++) {
         if ((nblobs << lg) > (size_t)d->max_partials) break;          // one XYZZ partial per warp
         const double warps = (double)(nblobs << lg);
         const double waves = std::ceil(warps / slots);
@@ -404,8 +427,21 @@ void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint3
     p.splits_log2 = pick_splits_log2(d, (size_t)n);
     p.partials = s.d_partials; p.bad = bad;
     const long long warps = (long long)n << p.splits_log2;
+    // entries per lane; the affine kernel needs a few rounds of `chains` entries to pay for its
+    // per-round inversion and the final chain sums
+    const int per_lane_entries = ((NPTS >> p.splits_log2) >> 5) * d->geom.W;
+    const bool affine = d->msm_affine && d->aff_scratch && per_lane_entries >= d->aff_min_entries;
     timer_begin(d, d->s_main, T_MSM);
-    launch_k_msm((unsigned)((warps + 7) / 8), 256, 0, d->s_main, p);
+    if (affine) {
+        MsmAffParams q;
+        q.table = p.table; q.g = p.g; q.scalars = p.scalars; q.nblobs = n; q.splits_log2 = p.splits_log2;
+        q.partials = p.partials; q.bad = p.bad; q.scratch = d->aff_scratch; q.K = d->aff_chains;
+        q.ngroups = (int)((warps + 7) / 8);
+        memcpy(q.H, d->recode_h, sizeof q.H);
+        launch_k_msm_affine((unsigned)std::min<long long>(q.ngroups, d->sm_count), 256, (size_t)q.K * 256 * 4, d->s_main, q);
+    } else {
+        launch_k_msm((unsigned)((warps + 7) / 8), 256, 0, d->s_main, p);
+    }
     timer_end(d, d->s_main);
     d->stats.msm_point_adds += (uint64_t)n * NPTS * d->geom.W;
     *splits_out = 1 << p.splits_log2;

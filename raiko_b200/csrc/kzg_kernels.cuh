@@ -179,8 +179,313 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
     }
     if (live && lane == 0) prm.partials[warp] = acc;
 }
+#endif  // RK_TU_MSM (xyzz body)
 
+// ---------------------------------------------------------------------------
+// k_msm_affine: the same MSM with batched AFFINE additions.
+//
+// An affine addition costs 1 inversion + 2 M + 1 S; sharing the inversion over K independent
+// additions (Montgomery's trick: 3 M per element) makes it 5 M + 1 S + I/K against the 8 M + 2 S
+// of the inversion-free XYZZ form -- a win once I is cheap, and field30.cuh's division-step
+// inversion is ~35 M.  Independence comes from splitting each lane's 128 * W table entries over
+// K <= 64 chains (entry e belongs to chain e mod K), each chain an affine running sum:
+//   forward  (k = 0..K-1):   d_k = x2_k - x1_k,  save P_{k-1},  P_k = P_{k-1} d_k        1 M
+//   invert   I = 1 / P_{K-1}                                                             ~35 M / K
+//   backward (k = K-1..0):   1/d_k = I P_{k-1},  I = I d_k,  lambda, x3, y3             4 M + 1 S
+// K = 64: 6.3 M-equivalents per addition instead of 9.6.
+//
+// The chain sums and prefix products do not fit on chip (64 x 156 B per thread), so they live
+// in a per-CTA scratch area in HBM laid out [chain][word][thread]: every access is a fully
+// coalesced 128-byte line per warp, streamed once per round and prefetched one chain ahead
+// (~550 B of traffic per addition, ~2 TB/s at full speed: a third of HBM3e, hidden behind the
+// multiplies).  The kernel is persistent (one CTA per SM) so the scratch is indexed by SM slot.
+// Scalars are recoded by the add-constant trick (s + H, H = sum half * 2^(cj)) so that a digit
+// can be read at any position without a carry chain; digits of a round are staged in shared
+// memory.  Exceptional additions (equal x: doubling or cancellation) cannot occur between
+// distinct setup points without knowing their discrete logs, but are handled exactly anyway
+// (affine_add_rare), as are empty digits and empty chains.
+// ---------------------------------------------------------------------------
+struct MsmAffParams {
+    const TableEntry* table;
+    TableGeom g;
+    const uint8_t* scalars;
+    int nblobs;
+    int splits_log2;
+    G1Xyzz* partials;
+    uint32_t* bad;
+    uint32_t* scratch;        // gridDim.x * K * AFF_WORDS * 256 words
+    int K;                    // chains per lane, 1..64
+    int ngroups;              // groups of 8 warps (one CTA pass each)
+    uint32_t H[8];            // recoding constant, little-endian words
+};
+constexpr int AFF_WORDS = 39;   // per chain and thread: x[13] y[13] prefix[13]
+constexpr int MSM_AFF_MAX_K = 64;
 
+#ifdef RK_TU_MSM
+// (x1, y1) += (x2, y2) when x1 == x2 mod p: doubling or cancellation.  Returns false for infinity.
+static __device__ __noinline__ bool affine_add_rare(Fp& x1, Fp& y1, const Fp& x2, const Fp& y2) {
+    G1Xyzz a;
+    fe_set(a.x, x1); fe_set(a.y, y1);
+    fe_const<FpTag, FP_ONE>(a.zz); fe_const<FpTag, FP_ONE>(a.zzz);
+    g1_madd(a, x2, y2);
+    if (g1_is_inf(a)) return false;
+    Fp inv;
+    fe_inv_safegcd(inv, a.zzz);
+    G1Affine r;
+    g1_to_affine_with_inv(r, a, inv);
+    fe_set(x1, r.x); fe_set(y1, r.y);
+    return true;
+}
+
+__device__ __forceinline__ void unpack_entry_x(Fp& x, const uint4 (&t)[3]) {
+    uint32_t w[12] = {t[0].x, t[0].y, t[0].z, t[0].w, t[1].x, t[1].y, t[1].z, t[1].w, t[2].x, t[2].y, t[2].z, t[2].w};
+    fe_unpack<FpTag>(x, w);
+}
+
+template <int SYNC>
+__device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
+    extern __shared__ uint32_t sh_code[];          // [K][256]: table entry index + 1, bit 31 = negate; 0 = no entry
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int K = prm.K;
+    const int c = prm.g.c, W = prm.g.W;
+    const uint32_t half = prm.g.half, cmask = (1u << c) - 1u;
+    uint32_t* const scr = prm.scratch + (size_t)blockIdx.x * K * AFF_WORDS * 256 + tid;
+    const int pts_per_warp = NPTS >> prm.splits_log2;
+    const int per_lane = pts_per_warp >> 5;
+    const int total = per_lane * W;
+    const int rounds = (total + K - 1) / K;
+
+    for (int group = blockIdx.x; group < prm.ngroups; group += gridDim.x) {
+        const int warp = group * 8 + (tid >> 5);
+        const int blob_raw = warp >> prm.splits_log2;
+        const bool live = blob_raw < prm.nblobs;
+        const int blob = live ? blob_raw : prm.nblobs - 1;
+        const int split = warp & ((1 << prm.splits_log2) - 1);
+        const uint8_t* sc = prm.scalars + (size_t)blob * BLOB_BYTES;
+        const int first_pt = split * pts_per_warp + lane;
+        unsigned long long has = 0;
+        bool any_bad = false;
+
+        for (int rho = 0; rho < rounds; rho++) {
+            // ---- digits of this round's K entries -> shared ----------------------------------
+            {
+                int e = rho * K;
+                int t = e / W, j = e - t * W;
+                uint32_t s[8];
+                bool loaded = false;
+                for (int k = 0; k < K; k++, e++) {
+                    uint32_t code = 0;
+                    if (e < total) {
+                        const int pt = first_pt + 32 * t;
+                        if (!loaded || j == 0) {
+                            load_scalar_be(s, sc + 32 * pt);
+                            if (j == 0) any_bad |= scalar_geq_r(s);
+                            uint32_t cy = 0;
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                uint64_t v = (uint64_t)s[q] + prm.H[q] + cy;
+                                s[q] = (uint32_t)v; cy = (uint32_t)(v >> 32);
+                            }
+                            for (int q = 0; q < j; q++) {
+#pragma unroll
+                                for (int m = 0; m < 7; m++) s[m] = __funnelshift_r(s[m], s[m + 1], c);
+                                s[7] >>= c;
+                            }
+                            loaded = true;
+                        }
+                        uint32_t idx;
+                        bool neg = false;
+                        if (j < W - 1) {
+                            const int sd = (int)(s[0] & cmask) - (int)half;      // in [-half, half)
+#pragma unroll
+                            for (int m = 0; m < 7; m++) s[m] = __funnelshift_r(s[m], s[m + 1], c);
+                            s[7] >>= c;
+                            neg = sd < 0;
+                            idx = (uint32_t)(neg ? -sd : sd);
+                        } else {
+                            idx = s[0];
+                            if (idx > prm.g.top_entries) idx = 0;   // only a scalar >= r gets here: blob is rejected anyway
+                        }
+                        if (idx != 0) code = ((uint32_t)pt * prm.g.per_point + (uint32_t)j * half + idx) | (neg ? 0x80000000u : 0u);
+                        if (++j == W) { j = 0; t++; }
+                    }
+                    sh_code[k * 256 + tid] = code;
+                }
+            }
+
+            // ---- forward: prefix products of the denominators ------------------------------
+            Fp P;
+            fe_const<FpTag, FP_ONE>(P);
+            unsigned long long act = 0;
+            uint32_t code_n = sh_code[tid];
+            uint4 tx_n[3];
+            uint32_t x1_n[FP_N];
+            {
+                if (code_n) {
+                    const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code_n & 0x7fffffffu) - 1u));
+#pragma unroll
+                    for (int q = 0; q < 3; q++) tx_n[q] = ldg_nc(ep + q);
+                    if (has & 1ull) {
+#pragma unroll
+                        for (int q = 0; q < FP_N; q++) x1_n[q] = scr[(size_t)q * 256];
+                    }
+                }
+            }
+            for (int k = 0; k < K; k++) {
+                if (SYNC) __syncthreads();
+                const uint32_t code = code_n;
+                uint4 tx[3];
+                Fp x1;
+#pragma unroll
+                for (int q = 0; q < 3; q++) tx[q] = tx_n[q];
+#pragma unroll
+                for (int q = 0; q < FP_N; q++) x1.v[q] = x1_n[q];
+                if (k + 1 < K) {
+                    code_n = sh_code[(k + 1) * 256 + tid];
+                    if (code_n) {
+                        const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code_n & 0x7fffffffu) - 1u));
+#pragma unroll
+                        for (int q = 0; q < 3; q++) tx_n[q] = ldg_nc(ep + q);
+                        if ((has >> (k + 1)) & 1ull) {
+                            const uint32_t* a = scr + (size_t)(k + 1) * AFF_WORDS * 256;
+#pragma unroll
+                            for (int q = 0; q < FP_N; q++) x1_n[q] = a[(size_t)q * 256];
+                        }
+                    }
+                }
+                if (!code) continue;
+                uint32_t* const a = scr + (size_t)k * AFF_WORDS * 256;
+                Fp x2;
+                unpack_entry_x(x2, tx);
+                const bool negate = (code >> 31) != 0;
+                if (!((has >> k) & 1ull)) {
+                    // first entry of this chain: the sum is the table point itself
+                    const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code & 0x7fffffffu) - 1u));
+                    uint4 ty[3];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) ty[q] = ldg_nc(ep + 3 + q);
+                    Fp y2;
+                    unpack_entry_x(y2, ty);
+                    if (negate) fe_neg<FpTag, 2>(y2, y2);
+#pragma unroll
+                    for (int q = 0; q < FP_N; q++) { a[(size_t)q * 256] = x2.v[q]; a[(size_t)(FP_N + q) * 256] = y2.v[q]; }
+                    has |= 1ull << k;
+                    continue;
+                }
+                Fp d;
+                fe_sub<FpTag, 2>(d, x2, x1);
+                if (fe_is_zero_mod(d)) {
+                    const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code & 0x7fffffffu) - 1u));
+                    uint4 ty[3];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) ty[q] = ldg_nc(ep + 3 + q);
+                    Fp y2, y1;
+                    unpack_entry_x(y2, ty);
+                    if (negate) fe_neg<FpTag, 2>(y2, y2);
+#pragma unroll
+                    for (int q = 0; q < FP_N; q++) y1.v[q] = a[(size_t)(FP_N + q) * 256];
+                    if (affine_add_rare(x1, y1, x2, y2)) {
+#pragma unroll
+                        for (int q = 0; q < FP_N; q++) { a[(size_t)q * 256] = x1.v[q]; a[(size_t)(FP_N + q) * 256] = y1.v[q]; }
+                    } else {
+                        has &= ~(1ull << k);
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int q = 0; q < FP_N; q++) a[(size_t)(2 * FP_N + q) * 256] = P.v[q];
+                fe_mul(P, P, d);
+                act |= 1ull << k;
+            }
+
+            // ---- one inversion for the whole round ----------------------------------------------
+            Fp I;
+            fe_zero(I);
+            if (act) fe_inv_safegcd(I, P);
+
+            // ---- backward: peel the inverses off, finish the additions ----------------------
+            uint32_t pb_n[FP_N], xy_n[2 * FP_N];
+            uint4 te_n[6];
+            auto issue = [&](int k) {
+                if ((act >> k) & 1ull) {
+                    const uint32_t cd = sh_code[k * 256 + tid];
+                    const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((cd & 0x7fffffffu) - 1u));
+#pragma unroll
+                    for (int q = 0; q < 6; q++) te_n[q] = ldg_nc(ep + q);
+                    const uint32_t* a = scr + (size_t)k * AFF_WORDS * 256;
+#pragma unroll
+                    for (int q = 0; q < FP_N; q++) pb_n[q] = a[(size_t)(2 * FP_N + q) * 256];
+#pragma unroll
+                    for (int q = 0; q < 2 * FP_N; q++) xy_n[q] = a[(size_t)q * 256];
+                }
+            };
+            issue(K - 1);
+            for (int k = K - 1; k >= 0; k--) {
+                if (SYNC) __syncthreads();
+                Fp pb, x1, y1;
+                uint4 te[6];
+#pragma unroll
+                for (int q = 0; q < FP_N; q++) { pb.v[q] = pb_n[q]; x1.v[q] = xy_n[q]; y1.v[q] = xy_n[FP_N + q]; }
+#pragma unroll
+                for (int q = 0; q < 6; q++) te[q] = te_n[q];
+                if (k > 0) issue(k - 1);
+                if (!((act >> k) & 1ull)) continue;
+                const bool negate = (sh_code[k * 256 + tid] >> 31) != 0;
+                Fp inv, x2, y2, d, lam, t;
+                fe_mul(inv, I, pb);                        // 1 / d_k
+                {
+                    uint32_t w[24];
+#pragma unroll
+                    for (int q = 0; q < 6; q++) { w[4 * q] = te[q].x; w[4 * q + 1] = te[q].y; w[4 * q + 2] = te[q].z; w[4 * q + 3] = te[q].w; }
+                    fe_unpack<FpTag>(x2, w);
+                    fe_unpack<FpTag>(y2, w + 12);
+                }
+                if (negate) fe_neg<FpTag, 2>(y2, y2);      // < 2p
+                fe_sub<FpTag, 2>(d, x2, x1);               // x1 < 1.2p
+                fe_mul(I, I, d);
+                fe_sub<FpTag, 2>(t, y2, y1);               // y1 <= 2p; < 4p
+                fe_mul(lam, t, inv);
+                fe_sqr(t, lam);
+                fe_add(x2, x2, x1);                        // < 2.4p
+                fe_sub<FpTag, 3>(t, t, x2);                // x3 < 4.2p
+                fe_reduce_loose<FpTag>(t);                 // < 1.0001p
+                fe_sub<FpTag, 2>(x1, x1, t);               // x1 - x3 < 3.2p
+                fe_mul(x1, lam, x1);
+                fe_sub<FpTag, 2>(y1, x1, y1);              // y3 < 3.2p
+                fe_reduce_loose<FpTag>(y1);
+                uint32_t* const a = scr + (size_t)k * AFF_WORDS * 256;
+#pragma unroll
+                for (int q = 0; q < FP_N; q++) { a[(size_t)q * 256] = t.v[q]; a[(size_t)(FP_N + q) * 256] = y1.v[q]; }
+            }
+        }
+
+        // ---- K chain sums -> one XYZZ sum per lane -> one per warp -----------------------------
+        G1Xyzz acc;
+        g1_set_inf(acc);
+        for (int k = 0; k < K; k++) {
+            if (SYNC) __syncthreads();
+            if (!((has >> k) & 1ull)) continue;
+            const uint32_t* a = scr + (size_t)k * AFF_WORDS * 256;
+            Fp x, y;
+#pragma unroll
+            for (int q = 0; q < FP_N; q++) { x.v[q] = a[(size_t)q * 256]; y.v[q] = a[(size_t)(FP_N + q) * 256]; }
+            g1_madd(acc, x, y);
+        }
+        if (live && prm.bad != nullptr && __any_sync(0xffffffffu, any_bad) && lane == 0) atomicOr(prm.bad + blob, 1u);
+        for (int delta = 16; delta >= 1; delta >>= 1) {
+            G1Xyzz o;
+            shfl_fp(o.x, acc.x, delta); shfl_fp(o.y, acc.y, delta);
+            shfl_fp(o.zz, acc.zz, delta); shfl_fp(o.zzz, acc.zzz, delta);
+            if (lane < delta) g1_add(acc, o);
+        }
+        if (live && lane == 0) prm.partials[warp] = acc;
+    }
+}
+
+__global__ void __maxnreg__(248) k_msm_affine(MsmAffParams prm) { msm_affine_body<1>(prm); }
+#endif  // RK_TU_MSM (affine)
+
+#ifdef RK_TU_MSM
 // 8 warps/SM x 248 registers with the lockstep barrier is the fastest configuration measured on
 // B200 (2.35 G additions/s); 12 warps x 168 registers 2.2-2.3, 16 warps x 128 registers 2.2,
 // no barrier 1.94, out-of-line multiplies 1.92 (profiles/r01/).  248 registers (not 255): 8 warps

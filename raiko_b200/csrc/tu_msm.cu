@@ -3,4 +3,7 @@
 #include "kzg_launch.h"
 namespace rk {
 RK_KERNELS_MSM(RK_DEFINE_LAUNCH)
+cudaError_t configure_k_msm_affine() {
+    return cudaFuncSetAttribute(k_msm_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 256 * 4);
+}
 }  // namespace rk

@@ -22,6 +22,10 @@ void fc_fr_unpack(const uint32_t* w, uint32_t* a) { Fr x; fe_unpack<FrTag>(x, w)
 void fc_fp_inv(const uint32_t* w, uint32_t* out) { Fp x, m, i, c; fe_unpack<FpTag>(x, w); fe_to_mont(m, x); fe_inv(i, m); fe_from_mont(c, i); fe_pack<FpTag>(out, c); }
 void fc_fr_inv(const uint32_t* w, uint32_t* out) { Fr x, m, i, c; fe_unpack<FrTag>(x, w); fe_to_mont(m, x); fe_inv(i, m); fe_from_mont(c, i); fe_pack<FrTag>(out, c); }
 
+// safegcd inversion: raw Montgomery limbs in (< 8 mod), raw Montgomery limbs out
+void fc_fp_inv_safegcd(const uint32_t* a, uint32_t* r) { Fp x, z; memcpy(x.v, a, 52); fe_inv_safegcd(z, x); memcpy(r, z.v, 52); }
+void fc_fr_inv_safegcd(const uint32_t* a, uint32_t* r) { Fr x, z; memcpy(x.v, a, 36); fe_inv_safegcd(z, x); memcpy(r, z.v, 36); }
+
 // G1: points travel as 48-byte compressed encodings
 static int load(G1Xyzz& p, const uint8_t* c) {
     G1Affine a; int rc = g1_decompress(a, c);
