@@ -112,6 +112,8 @@ struct DeviceCtx {
     // enough table entries to fill the chains, 0 = XYZZ only (k_msm).  RAIKO_KZG_MSM_AFFINE.
     int msm_affine = 1;
     int aff_chains = MSM_AFF_MAX_K;
+    bool aff_lockstep = true;                  // CTA-wide barrier per chain step (one instruction fetch serves all warps)
+    int aff_warps = 16;                        // warps per CTA of the affine kernel: 8 (248 regs), 12 (168), 16 (128)
     int aff_min_entries = 8 * MSM_AFF_MAX_K;   // per-lane table entries below which k_msm is used
     int max_splits_log2 = 7;                   // test knob: 0 forces one warp per blob
     uint32_t* aff_scratch = nullptr;       // sm_count x chains x 39 words x 256 threads
@@ -313,13 +315,15 @@ rk_status alloc_slots(DeviceCtx* d) {
     }
     d->max_partials = std::max(16 * d->chunk, 128 * 128);
     if (const char* e = getenv("RAIKO_KZG_MSM_AFFINE")) d->msm_affine = atoi(e);
-    if (const char* e = getenv("RAIKO_KZG_AFFINE_CHAINS")) d->aff_chains = std::min(MSM_AFF_MAX_K, std::max(1, atoi(e)));
+    if (const char* e = getenv("RAIKO_KZG_AFFINE_CHAINS")) d->aff_chains = std::min(MSM_AFF_MAX_K, std::max(2, atoi(e) & ~1));
+    if (const char* e = getenv("RAIKO_KZG_AFFINE_WARPS")) { int v = atoi(e); if (v == 8 || v == 12 || v == 16) d->aff_warps = v; }
+    if (const char* e = getenv("RAIKO_KZG_AFFINE_LOCKSTEP")) d->aff_lockstep = atoi(e) != 0;
     d->aff_min_entries = 8 * d->aff_chains;
     if (const char* e = getenv("RAIKO_KZG_AFFINE_MIN_ENTRIES")) d->aff_min_entries = std::max(1, atoi(e));
     if (const char* e = getenv("RAIKO_KZG_MAX_SPLITS_LOG2")) d->max_splits_log2 = std::min(7, std::max(0, atoi(e)));
     if (d->msm_affine) {
         CUDA_TRY(configure_k_msm_affine());
-        CUDA_TRY(cudaMalloc(&d->aff_scratch, (size_t)d->sm_count * d->aff_chains * AFF_WORDS * 256 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&d->aff_scratch, (size_t)d->sm_count * d->aff_chains * AFF_WORDS * (32 * d->aff_warps) * sizeof(uint32_t)));
         // H = sum_{j < W-1} 2^(c-1) * 2^(cj): adding it turns unsigned digits into signed ones
         memset(d->recode_h, 0, sizeof d->recode_h);
         for (int j = 0; j < d->geom.W - 1; j++) {
@@ -436,9 +440,15 @@ void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint3
         MsmAffParams q;
         q.table = p.table; q.g = p.g; q.scalars = p.scalars; q.nblobs = n; q.splits_log2 = p.splits_log2;
         q.partials = p.partials; q.bad = p.bad; q.scratch = d->aff_scratch; q.K = d->aff_chains;
-        q.ngroups = (int)((warps + 7) / 8);
+        const int wpc = d->aff_warps, threads = 32 * wpc;
+        q.ngroups = (int)((warps + wpc - 1) / wpc);
         memcpy(q.H, d->recode_h, sizeof q.H);
-        launch_k_msm_affine((unsigned)std::min<long long>(q.ngroups, d->sm_count), 256, (size_t)q.K * 256 * 4, d->s_main, q);
+        const unsigned grid = (unsigned)std::min<long long>(q.ngroups, d->sm_count);
+        const size_t smem = (size_t)q.K * threads * 4;
+        if (wpc == 8) launch_k_msm_affine(grid, threads, smem, d->s_main, q);
+        else if (wpc == 12) launch_k_msm_affine_w12(grid, threads, smem, d->s_main, q);
+        else if (d->aff_lockstep) launch_k_msm_affine_w16(grid, threads, smem, d->s_main, q);
+        else launch_k_msm_affine_w16n(grid, threads, smem, d->s_main, q);
     } else {
         launch_k_msm((unsigned)((warps + 7) / 8), 256, 0, d->s_main, p);
     }

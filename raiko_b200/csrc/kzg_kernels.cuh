@@ -213,9 +213,9 @@ struct MsmAffParams {
     int splits_log2;
     G1Xyzz* partials;
     uint32_t* bad;
-    uint32_t* scratch;        // gridDim.x * K * AFF_WORDS * 256 words
+    uint32_t* scratch;        // gridDim.x * K * AFF_WORDS * block size words
     int K;                    // chains per lane, 1..64
-    int ngroups;              // groups of 8 warps (one CTA pass each)
+    int ngroups;              // groups of block-size / 32 warps (one CTA pass each)
     uint32_t H[8];            // recoding constant, little-endian words
 };
 constexpr int AFF_WORDS = 39;   // per chain and thread: x[13] y[13] prefix[13]
@@ -242,21 +242,57 @@ __device__ __forceinline__ void unpack_entry_x(Fp& x, const uint4 (&t)[3]) {
     fe_unpack<FpTag>(x, w);
 }
 
-template <int SYNC>
+// Scratch of one chain for one CTA: nine uint4 planes (x, y, prefix: limbs 0..11) followed by
+// three word planes (limb 12 of each), every plane THREADS wide -> each access is one fully
+// coalesced line per warp and a field element moves in 3 x 128-bit + 1 x 32-bit accesses.
+template <int THREADS>
+struct ChainScratch {
+    uint4* v;
+    uint32_t* w;
+    __device__ __forceinline__ ChainScratch(uint32_t* base, int k, int tid) {
+        uint32_t* c = base + (size_t)k * (AFF_WORDS * THREADS);
+        v = reinterpret_cast<uint4*>(c) + tid;
+        w = c + 36 * THREADS + tid;
+    }
+};
+struct FpRaw {                       // a field element as it travels: no arithmetic meaning
+    uint4 q[3];
+    uint32_t top;
+};
+template <int THREADS>
+__device__ __forceinline__ void chain_load(FpRaw& r, const ChainScratch<THREADS>& c, int g) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) r.q[i] = c.v[(size_t)(3 * g + i) * THREADS];
+    r.top = c.w[(size_t)g * THREADS];
+}
+template <int THREADS>
+__device__ __forceinline__ void chain_store(const ChainScratch<THREADS>& c, int g, const Fp& a) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) c.v[(size_t)(3 * g + i) * THREADS] = make_uint4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+    c.w[(size_t)g * THREADS] = a.v[12];
+}
+__device__ __forceinline__ void raw_to_fp(Fp& a, const FpRaw& r) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { a.v[4 * i] = r.q[i].x; a.v[4 * i + 1] = r.q[i].y; a.v[4 * i + 2] = r.q[i].z; a.v[4 * i + 3] = r.q[i].w; }
+    a.v[12] = r.top;
+}
+
+template <int THREADS, int SYNC>
 __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
-    extern __shared__ uint32_t sh_code[];          // [K][256]: table entry index + 1, bit 31 = negate; 0 = no entry
+    extern __shared__ uint32_t sh_code[];          // [K][THREADS]: table entry index + 1, bit 31 = negate; 0 = no entry
     const int tid = threadIdx.x, lane = tid & 31;
-    const int K = prm.K;
+    const int K = prm.K;                           // even
     const int c = prm.g.c, W = prm.g.W;
     const uint32_t half = prm.g.half, cmask = (1u << c) - 1u;
-    uint32_t* const scr = prm.scratch + (size_t)blockIdx.x * K * AFF_WORDS * 256 + tid;
+    uint32_t* const scr = prm.scratch + (size_t)blockIdx.x * K * (AFF_WORDS * THREADS);
     const int pts_per_warp = NPTS >> prm.splits_log2;
     const int per_lane = pts_per_warp >> 5;
     const int total = per_lane * W;
     const int rounds = (total + K - 1) / K;
+    constexpr int WARPS = THREADS / 32;
 
     for (int group = blockIdx.x; group < prm.ngroups; group += gridDim.x) {
-        const int warp = group * 8 + (tid >> 5);
+        const int warp = group * WARPS + (tid >> 5);
         const int blob_raw = warp >> prm.splits_log2;
         const bool live = blob_raw < prm.nblobs;
         const int blob = live ? blob_raw : prm.nblobs - 1;
@@ -309,91 +345,62 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
                         if (idx != 0) code = ((uint32_t)pt * prm.g.per_point + (uint32_t)j * half + idx) | (neg ? 0x80000000u : 0u);
                         if (++j == W) { j = 0; t++; }
                     }
-                    sh_code[k * 256 + tid] = code;
+                    sh_code[k * THREADS + tid] = code;
                 }
             }
 
             // ---- forward: prefix products of the denominators ------------------------------
+            // No software prefetch anywhere in this kernel: it is latency-bound, not pipe-bound, so
+            // the registers buy more as extra resident warps (16 per SM) than as load buffers.
             Fp P;
             fe_const<FpTag, FP_ONE>(P);
             unsigned long long act = 0;
-            uint32_t code_n = sh_code[tid];
-            uint4 tx_n[3];
-            uint32_t x1_n[FP_N];
-            {
-                if (code_n) {
-                    const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code_n & 0x7fffffffu) - 1u));
-#pragma unroll
-                    for (int q = 0; q < 3; q++) tx_n[q] = ldg_nc(ep + q);
-                    if (has & 1ull) {
-#pragma unroll
-                        for (int q = 0; q < FP_N; q++) x1_n[q] = scr[(size_t)q * 256];
-                    }
-                }
-            }
             for (int k = 0; k < K; k++) {
                 if (SYNC) __syncthreads();
-                const uint32_t code = code_n;
-                uint4 tx[3];
-                Fp x1;
-#pragma unroll
-                for (int q = 0; q < 3; q++) tx[q] = tx_n[q];
-#pragma unroll
-                for (int q = 0; q < FP_N; q++) x1.v[q] = x1_n[q];
-                if (k + 1 < K) {
-                    code_n = sh_code[(k + 1) * 256 + tid];
-                    if (code_n) {
-                        const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code_n & 0x7fffffffu) - 1u));
-#pragma unroll
-                        for (int q = 0; q < 3; q++) tx_n[q] = ldg_nc(ep + q);
-                        if ((has >> (k + 1)) & 1ull) {
-                            const uint32_t* a = scr + (size_t)(k + 1) * AFF_WORDS * 256;
-#pragma unroll
-                            for (int q = 0; q < FP_N; q++) x1_n[q] = a[(size_t)q * 256];
-                        }
-                    }
-                }
+                const uint32_t code = sh_code[k * THREADS + tid];
                 if (!code) continue;
-                uint32_t* const a = scr + (size_t)k * AFF_WORDS * 256;
+                const ChainScratch<THREADS> cs(scr, k, tid);
+                const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code & 0x7fffffffu) - 1u));
                 Fp x2;
-                unpack_entry_x(x2, tx);
-                const bool negate = (code >> 31) != 0;
-                if (!((has >> k) & 1ull)) {
-                    // first entry of this chain: the sum is the table point itself
-                    const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code & 0x7fffffffu) - 1u));
+                {
+                    uint4 tx[3];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) tx[q] = ldg_nc(ep + q);
+                    unpack_entry_x(x2, tx);
+                }
+                const bool first = !((has >> k) & 1ull);
+                Fp d, x1;
+                bool rare = false;
+                if (!first) {
+                    FpRaw xr;
+                    chain_load<THREADS>(xr, cs, 0);
+                    raw_to_fp(x1, xr);
+                    fe_sub<FpTag, 2>(d, x2, x1);
+                    rare = fe_is_zero_mod(d);
+                }
+                if (first || rare) {
+                    // first entry of a chain (the sum is the table point itself), or equal x:
+                    // doubling / cancellation, handled outside the batch
                     uint4 ty[3];
 #pragma unroll
                     for (int q = 0; q < 3; q++) ty[q] = ldg_nc(ep + 3 + q);
                     Fp y2;
                     unpack_entry_x(y2, ty);
-                    if (negate) fe_neg<FpTag, 2>(y2, y2);
-#pragma unroll
-                    for (int q = 0; q < FP_N; q++) { a[(size_t)q * 256] = x2.v[q]; a[(size_t)(FP_N + q) * 256] = y2.v[q]; }
-                    has |= 1ull << k;
-                    continue;
-                }
-                Fp d;
-                fe_sub<FpTag, 2>(d, x2, x1);
-                if (fe_is_zero_mod(d)) {
-                    const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code & 0x7fffffffu) - 1u));
-                    uint4 ty[3];
-#pragma unroll
-                    for (int q = 0; q < 3; q++) ty[q] = ldg_nc(ep + 3 + q);
-                    Fp y2, y1;
-                    unpack_entry_x(y2, ty);
-                    if (negate) fe_neg<FpTag, 2>(y2, y2);
-#pragma unroll
-                    for (int q = 0; q < FP_N; q++) y1.v[q] = a[(size_t)(FP_N + q) * 256];
-                    if (affine_add_rare(x1, y1, x2, y2)) {
-#pragma unroll
-                        for (int q = 0; q < FP_N; q++) { a[(size_t)q * 256] = x1.v[q]; a[(size_t)(FP_N + q) * 256] = y1.v[q]; }
-                    } else {
-                        has &= ~(1ull << k);
+                    if (code >> 31) fe_neg<FpTag, 2>(y2, y2);
+                    bool keep = true;
+                    if (rare) {
+                        FpRaw yr;
+                        chain_load<THREADS>(yr, cs, 1);
+                        Fp y1;
+                        raw_to_fp(y1, yr);
+                        keep = affine_add_rare(x1, y1, x2, y2);
+                        fe_set(x2, x1); fe_set(y2, y1);
                     }
+                    if (keep) { chain_store<THREADS>(cs, 0, x2); chain_store<THREADS>(cs, 1, y2); has |= 1ull << k; }
+                    else has &= ~(1ull << k);
                     continue;
                 }
-#pragma unroll
-                for (int q = 0; q < FP_N; q++) a[(size_t)(2 * FP_N + q) * 256] = P.v[q];
+                chain_store<THREADS>(cs, 2, P);
                 fe_mul(P, P, d);
                 act |= 1ull << k;
             }
@@ -404,58 +411,64 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
             if (act) fe_inv_safegcd(I, P);
 
             // ---- backward: peel the inverses off, finish the additions ----------------------
-            uint32_t pb_n[FP_N], xy_n[2 * FP_N];
-            uint4 te_n[6];
-            auto issue = [&](int k) {
-                if ((act >> k) & 1ull) {
-                    const uint32_t cd = sh_code[k * 256 + tid];
-                    const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((cd & 0x7fffffffu) - 1u));
-#pragma unroll
-                    for (int q = 0; q < 6; q++) te_n[q] = ldg_nc(ep + q);
-                    const uint32_t* a = scr + (size_t)k * AFF_WORDS * 256;
-#pragma unroll
-                    for (int q = 0; q < FP_N; q++) pb_n[q] = a[(size_t)(2 * FP_N + q) * 256];
-#pragma unroll
-                    for (int q = 0; q < 2 * FP_N; q++) xy_n[q] = a[(size_t)q * 256];
-                }
-            };
-            issue(K - 1);
+            // Operands are re-read from the scratch (L1/L2 hits) where that shortens a live range.
             for (int k = K - 1; k >= 0; k--) {
                 if (SYNC) __syncthreads();
-                Fp pb, x1, y1;
-                uint4 te[6];
-#pragma unroll
-                for (int q = 0; q < FP_N; q++) { pb.v[q] = pb_n[q]; x1.v[q] = xy_n[q]; y1.v[q] = xy_n[FP_N + q]; }
-#pragma unroll
-                for (int q = 0; q < 6; q++) te[q] = te_n[q];
-                if (k > 0) issue(k - 1);
                 if (!((act >> k) & 1ull)) continue;
-                const bool negate = (sh_code[k * 256 + tid] >> 31) != 0;
-                Fp inv, x2, y2, d, lam, t;
-                fe_mul(inv, I, pb);                        // 1 / d_k
+                const uint32_t code = sh_code[k * THREADS + tid];
+                const ChainScratch<THREADS> cs(scr, k, tid);
+                const uint4* ep = reinterpret_cast<const uint4*>(prm.table + ((code & 0x7fffffffu) - 1u));
+                Fp inv, lam, t, u;
                 {
-                    uint32_t w[24];
-#pragma unroll
-                    for (int q = 0; q < 6; q++) { w[4 * q] = te[q].x; w[4 * q + 1] = te[q].y; w[4 * q + 2] = te[q].z; w[4 * q + 3] = te[q].w; }
-                    fe_unpack<FpTag>(x2, w);
-                    fe_unpack<FpTag>(y2, w + 12);
+                    FpRaw r;
+                    chain_load<THREADS>(r, cs, 2);
+                    raw_to_fp(inv, r);
                 }
-                if (negate) fe_neg<FpTag, 2>(y2, y2);      // < 2p
-                fe_sub<FpTag, 2>(d, x2, x1);               // x1 < 1.2p
-                fe_mul(I, I, d);
-                fe_sub<FpTag, 2>(t, y2, y1);               // y1 <= 2p; < 4p
+                fe_mul(inv, I, inv);                       // 1 / d_k
+                {
+                    uint4 tx[3];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) tx[q] = ldg_nc(ep + q);
+                    unpack_entry_x(t, tx);                 // x2
+                    FpRaw r;
+                    chain_load<THREADS>(r, cs, 0);
+                    raw_to_fp(u, r);                       // x1 < 1.2p
+                }
+                fe_sub<FpTag, 2>(lam, t, u);               // d_k
+                fe_mul(I, I, lam);
+                fe_add(u, u, t);                           // x1 + x2 < 2.4p, kept for x3
+                {
+                    uint4 ty[3];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) ty[q] = ldg_nc(ep + 3 + q);
+                    unpack_entry_x(t, ty);                 // y2
+                    if (code >> 31) fe_neg<FpTag, 2>(t, t);    // < 2p
+                    FpRaw r;
+                    chain_load<THREADS>(r, cs, 1);
+                    Fp y1;
+                    raw_to_fp(y1, r);                      // <= 2p
+                    fe_sub<FpTag, 2>(t, t, y1);            // < 4p
+                }
                 fe_mul(lam, t, inv);
                 fe_sqr(t, lam);
-                fe_add(x2, x2, x1);                        // < 2.4p
-                fe_sub<FpTag, 3>(t, t, x2);                // x3 < 4.2p
+                fe_sub<FpTag, 3>(t, t, u);                 // x3 < 4.2p
                 fe_reduce_loose<FpTag>(t);                 // < 1.0001p
-                fe_sub<FpTag, 2>(x1, x1, t);               // x1 - x3 < 3.2p
-                fe_mul(x1, lam, x1);
-                fe_sub<FpTag, 2>(y1, x1, y1);              // y3 < 3.2p
-                fe_reduce_loose<FpTag>(y1);
-                uint32_t* const a = scr + (size_t)k * AFF_WORDS * 256;
-#pragma unroll
-                for (int q = 0; q < FP_N; q++) { a[(size_t)q * 256] = t.v[q]; a[(size_t)(FP_N + q) * 256] = y1.v[q]; }
+                {
+                    FpRaw r;
+                    chain_load<THREADS>(r, cs, 0);
+                    raw_to_fp(u, r);                       // x1 again
+                }
+                chain_store<THREADS>(cs, 0, t);
+                fe_sub<FpTag, 2>(u, u, t);                 // x1 - x3 < 3.2p
+                fe_mul(u, lam, u);
+                {
+                    FpRaw r;
+                    chain_load<THREADS>(r, cs, 1);
+                    raw_to_fp(t, r);                       // y1 again
+                }
+                fe_sub<FpTag, 2>(u, u, t);                 // y3 < 3.2p
+                fe_reduce_loose<FpTag>(u);
+                chain_store<THREADS>(cs, 1, u);
             }
         }
 
@@ -465,10 +478,13 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
         for (int k = 0; k < K; k++) {
             if (SYNC) __syncthreads();
             if (!((has >> k) & 1ull)) continue;
-            const uint32_t* a = scr + (size_t)k * AFF_WORDS * 256;
+            const ChainScratch<THREADS> cs(scr, k, tid);
+            FpRaw xr, yr;
+            chain_load<THREADS>(xr, cs, 0);
+            chain_load<THREADS>(yr, cs, 1);
             Fp x, y;
-#pragma unroll
-            for (int q = 0; q < FP_N; q++) { x.v[q] = a[(size_t)q * 256]; y.v[q] = a[(size_t)(FP_N + q) * 256]; }
+            raw_to_fp(x, xr);
+            raw_to_fp(y, yr);
             g1_madd(acc, x, y);
         }
         if (live && prm.bad != nullptr && __any_sync(0xffffffffu, any_bad) && lane == 0) atomicOr(prm.bad + blob, 1u);
@@ -482,7 +498,10 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
     }
 }
 
-__global__ void __maxnreg__(248) k_msm_affine(MsmAffParams prm) { msm_affine_body<1>(prm); }
+__global__ void __maxnreg__(248) k_msm_affine(MsmAffParams prm) { msm_affine_body<256, 1>(prm); }
+__global__ void __maxnreg__(168) k_msm_affine_w12(MsmAffParams prm) { msm_affine_body<384, 1>(prm); }
+__global__ void __maxnreg__(128) k_msm_affine_w16(MsmAffParams prm) { msm_affine_body<512, 1>(prm); }
+__global__ void __maxnreg__(128) k_msm_affine_w16n(MsmAffParams prm) { msm_affine_body<512, 0>(prm); }
 #endif  // RK_TU_MSM (affine)
 
 #ifdef RK_TU_MSM

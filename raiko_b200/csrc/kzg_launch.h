@@ -10,7 +10,10 @@ namespace rk {
 
 #define RK_KERNELS_MSM(X)                                                                      \
     X(k_msm, (MsmParams p), (p))                                                               \
-    X(k_msm_affine, (MsmAffParams p), (p))
+    X(k_msm_affine, (MsmAffParams p), (p))                                                     \
+    X(k_msm_affine_w12, (MsmAffParams p), (p))                                                 \
+    X(k_msm_affine_w16, (MsmAffParams p), (p))                                                 \
+    X(k_msm_affine_w16n, (MsmAffParams p), (p))
 
 #define RK_KERNELS_PATH(X)                                                                     \
     X(k_finalize, (const G1Xyzz* partials, int splits, int nblobs, const uint32_t* bad, uint8_t* out_g1, uint8_t* out_vh, uint8_t* status, int stride), \
@@ -58,7 +61,7 @@ RK_KERNELS_PATH(RK_DECLARE_LAUNCH)
 RK_KERNELS_TABLE(RK_DECLARE_LAUNCH)
 RK_KERNELS_VERIFY(RK_DECLARE_LAUNCH)
 RK_KERNELS_PAIRING(RK_DECLARE_LAUNCH)
-// opts k_msm_affine into its dynamic shared memory (digit codes: 4 B x 64 chains x 256 threads)
+// opts k_msm_affine into its dynamic shared memory (digit codes: 4 B x 64 chains x block size)
 cudaError_t configure_k_msm_affine();
 
 }  // namespace rk

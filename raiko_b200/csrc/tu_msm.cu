@@ -4,6 +4,10 @@
 namespace rk {
 RK_KERNELS_MSM(RK_DEFINE_LAUNCH)
 cudaError_t configure_k_msm_affine() {
-    return cudaFuncSetAttribute(k_msm_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 256 * 4);
+    cudaError_t e = cudaFuncSetAttribute(k_msm_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 256 * 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_msm_affine_w12, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 384 * 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_msm_affine_w16, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 512 * 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_msm_affine_w16n, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 512 * 4);
+    return e;
 }
 }  // namespace rk

@@ -13,7 +13,7 @@ from kzg_testlib import SETUP
 
 wb = int(sys.argv[1]) if len(sys.argv) > 1 else 15
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4736
-chains = [int(a) for a in sys.argv[3:]] or [64]
+chains = [a for a in sys.argv[3:]] or ["64"]     # "chains" or "chains:warps"
 lib = _native.load()
 g = torch.Generator(device="cuda"); g.manual_seed(7)
 blobs = torch.randint(0, 256, (n, 4096, 32), dtype=torch.uint8, device="cuda", generator=g)
@@ -24,7 +24,9 @@ results = {}
 for mode in [("xyzz", 0, 0)] + [("affine", 1, k) for k in chains]:
     os.environ["RAIKO_KZG_MSM_AFFINE"] = str(mode[1])
     if mode[2]:
-        os.environ["RAIKO_KZG_AFFINE_CHAINS"] = str(mode[2])
+        os.environ["RAIKO_KZG_AFFINE_CHAINS"] = mode[2].split(":")[0]
+        os.environ["RAIKO_KZG_AFFINE_WARPS"] = (mode[2].split(":") + ["8"])[1]
+        os.environ["RAIKO_KZG_AFFINE_LOCKSTEP"] = (mode[2].split(":") + ["8", "1"])[2]
     s = rk.KzgSettings(window_bits=wb)
     outs = {k: torch.zeros((n, w), dtype=torch.uint8, device="cuda") for k, w in (("c", 48), ("vh", 32), ("x", 32), ("y", 32), ("p", 48), ("st", 1))}
     def run():
@@ -34,7 +36,7 @@ for mode in [("xyzz", 0, 0)] + [("affine", 1, k) for k in chains]:
     s.stats_enable(True); s.stats_reset()
     t = time.time(); run(); torch.cuda.synchronize(); dt = time.time() - t
     st = s.stats(); s.stats_enable(False)
-    name = "%s%s" % (mode[0], "-%d" % mode[2] if mode[2] else "")
+    name = "%s%s" % (mode[0], "-" + mode[2] if mode[2] else "")
     print("%-10s c=%d n=%d: %.1f ms  %.0f blobs/s | msm %.1f ms (%d launches, %.3f G add/s) fr %.1f sha %.1f fin %.1f" % (
         name, s.window_bits, n, dt * 1e3, n / dt, st["msm_ms"], st["msm_launches"], st["msm_point_adds"] / st["msm_ms"] / 1e6,
         st["fr_ms"], st["sha_ms"], st["finalize_ms"]), flush=True)
