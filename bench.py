@@ -39,6 +39,10 @@ MODEL_IMAD_PER_BLOB = 1.09e9       # commit + proof: 2 MSM + Fr side
 # what this implementation actually issues on the integer-multiply pipe per table addition:
 # madd-2008-s = 8 M + 2 S on 13 x 30-bit limbs = 8*(2*169+13) + 2*(91+169+13) IMAD.WIDE/IMAD
 EXEC_IMAD_PER_ADD = 8 * 351 + 2 * 273
+# k_msm_affine (batched affine additions): 5 M + 1 S per addition, plus per 64 additions one
+# division-step inversion (27 iterations x 132 multiplies) and per 2176 additions 63 XYZZ
+# chain-sum additions
+EXEC_IMAD_PER_ADD_AFFINE = 5 * 351 + 273 + (27 * 132) // 64 + (63 * EXEC_IMAD_PER_ADD) // 2176
 
 
 def parse_args():
@@ -329,7 +333,9 @@ def run_ours(args):
     avg_launch_s = msm_s / msm_launches
     msm_per_launch = msms_done / msm_launches
     achieved = MODEL_IMAD_PER_MSM * msm_per_launch / avg_launch_s          # algorithmic IMAD/s (work model)
-    executed = EXEC_IMAD_PER_ADD * stats["msm_point_adds"] / msm_s        # issued on the multiply pipe
+    aff_adds = stats.get("msm_affine_point_adds", 0)
+    executed = (EXEC_IMAD_PER_ADD * (stats["msm_point_adds"] - aff_adds) + EXEC_IMAD_PER_ADD_AFFINE * aff_adds) / msm_s   # issued on the multiply pipe
+    msm_kernel = "k_msm_affine" if 2 * aff_adds > stats["msm_point_adds"] else "k_msm"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "msm_dram_traffic.json")
     if os.path.exists(tpath):
@@ -339,7 +345,7 @@ def run_ours(args):
             traffic = None
     geom_w = stats["msm_point_adds"] / max(1, msms_done) / 4096
     roofline = {
-        "bound": "imad", "kernel": "k_msm", "achieved": achieved / 1e12, "peak": peak.value / 1e12, "unit": "TIMAD/s",
+        "bound": "imad", "kernel": msm_kernel, "achieved": achieved / 1e12, "peak": peak.value / 1e12, "unit": "TIMAD/s",
         "frac": achieved / peak.value, "traffic": traffic,
         "peak_source": "measured in this run: dependency-free mad.wide.u32 on all SMs (rk_measure_imad_peak); MEASURED_PEAKS.json has no integer peak",
         "work_model": "SURVEY.md 8(d): 540.7e6 IMAD per 4096-term MSM (c=13 bucket Pippenger, 600 IMAD per Fp mul)",
@@ -348,6 +354,7 @@ def run_ours(args):
         "executed_timad_per_s": executed / 1e12, "frac_executed": executed / peak.value,
         "windows_per_scalar": geom_w,
         "table_read_gbs": stats["msm_point_adds"] * 96 / msm_s / 1e9,
+        "point_adds_per_s": stats["msm_point_adds"] / msm_s, "affine_share_of_adds": aff_adds / max(1, stats["msm_point_adds"]),
         "whole_path_frac": value / world * MODEL_IMAD_PER_BLOB / peak.value,
     }
 
@@ -357,9 +364,9 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         hbm_peak = 6650.0     # B200_PROFILING.md fallback
     alg_bytes_per_msm = 4096 * geom_w * 96 + BLOB          # table entries + the scalars
-    roofline_hbm = {"bound": "hbm", "kernel": "k_msm", "achieved": alg_bytes_per_msm * msm_per_launch / avg_launch_s / 1e9,
+    roofline_hbm = {"bound": "hbm", "kernel": msm_kernel, "achieved": alg_bytes_per_msm * msm_per_launch / avg_launch_s / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes_per_msm * msm_per_launch / avg_launch_s / 1e9 / hbm_peak,
-                    "traffic": traffic, "note": "random 96-byte table gathers; the kernel is multiply-pipe bound, not HBM bound"}
+                    "traffic": traffic, "note": "algorithmic bytes = one 96-byte table entry per addition + the scalars; k_msm_affine deliberately streams ~600 B more per addition (chain sums, prefix products) through HBM to save multiplies; the kernel is multiply/issue bound, not HBM bound"}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores -------------
     cpu = None

@@ -155,6 +155,9 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t msm_point_adds; /* table additions issued (non-zero digits are data dependent:
                                 this is the nominal count n * 4096 * windows)             */
+    uint64_t msm_affine_launches; /* MSM launches that used the batched-affine kernel
+                                (k_msm_affine); the rest used the XYZZ kernel (k_msm)     */
+    uint64_t msm_affine_point_adds; /* the part of msm_point_adds those launches issued   */
 } rk_kzg_stats;
 /* enable = 1 records a CUDA-event pair around every kernel (adds a little host time)     */
 void rk_kzg_stats_enable(rk_kzg_ctx* ctx, int enable);

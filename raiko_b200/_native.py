@@ -12,7 +12,8 @@ class RkKzgStats(ctypes.Structure):
     _fields_ = [("msm_ms", ctypes.c_double), ("fr_ms", ctypes.c_double), ("sha_ms", ctypes.c_double),
                 ("finalize_ms", ctypes.c_double), ("msm_launches", ctypes.c_uint64),
                 ("total_launches", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
-                ("msm_point_adds", ctypes.c_uint64)]
+                ("msm_point_adds", ctypes.c_uint64), ("msm_affine_launches", ctypes.c_uint64),
+                ("msm_affine_point_adds", ctypes.c_uint64)]
 
 
 _P = ctypes.c_void_p

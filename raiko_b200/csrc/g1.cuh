@@ -169,6 +169,24 @@ RK_HD void g1_to_affine_with_inv(G1Affine& r, const G1Xyzz& a, const Fp& zzz_inv
     fe_mul(r.y, a.y, zzz_inv);
 }
 
+// (x1, y1) += (x2, y2), both affine and finite, by way of the complete XYZZ addition and one
+// inversion: the fallback of the batched-affine MSM for the additions its shared-inversion
+// formula cannot do (equal x: doubling or cancellation).  Returns false when the sum is the
+// point at infinity.  Output coordinates < 1.2p.
+RK_HD_NOINLINE bool g1_affine_add_slow(Fp& x1, Fp& y1, const Fp& x2, const Fp& y2) {
+    G1Xyzz a;
+    fe_set(a.x, x1); fe_set(a.y, y1);
+    fe_const<FpTag, FP_ONE>(a.zz); fe_const<FpTag, FP_ONE>(a.zzz);
+    g1_madd(a, x2, y2);
+    if (g1_is_inf(a)) return false;
+    Fp inv;
+    fe_inv_safegcd(inv, a.zzz);
+    G1Affine r;
+    g1_to_affine_with_inv(r, a, inv);
+    fe_set(x1, r.x); fe_set(y1, r.y);
+    return true;
+}
+
 // r = k * p, k given as 8 little-endian 32-bit words (plain double-and-add; variable-base
 // work is off the throughput path: verification and tests only).
 RK_HD_NOINLINE void g1_scalar_mul(G1Xyzz& r, const G1Affine& p, const uint32_t* k) {

@@ -112,8 +112,7 @@ struct DeviceCtx {
     // enough table entries to fill the chains, 0 = XYZZ only (k_msm).  RAIKO_KZG_MSM_AFFINE.
     int msm_affine = 1;
     int aff_chains = MSM_AFF_MAX_K;
-    bool aff_lockstep = true;                  // CTA-wide barrier per chain step (one instruction fetch serves all warps)
-    int aff_warps = 16;                        // warps per CTA of the affine kernel: 8 (248 regs), 12 (168), 16 (128)
+    int aff_warps = MSM_AFF_THREADS / 32;      // warps per CTA of the affine kernel (one CTA per SM)
     int aff_min_entries = 8 * MSM_AFF_MAX_K;   // per-lane table entries below which k_msm is used
     int max_splits_log2 = 7;                   // test knob: 0 forces one warp per blob
     uint32_t* aff_scratch = nullptr;       // sm_count x chains x 39 words x 256 threads
@@ -316,8 +315,6 @@ rk_status alloc_slots(DeviceCtx* d) {
     d->max_partials = std::max(16 * d->chunk, 128 * 128);
     if (const char* e = getenv("RAIKO_KZG_MSM_AFFINE")) d->msm_affine = atoi(e);
     if (const char* e = getenv("RAIKO_KZG_AFFINE_CHAINS")) d->aff_chains = std::min(MSM_AFF_MAX_K, std::max(2, atoi(e) & ~1));
-    if (const char* e = getenv("RAIKO_KZG_AFFINE_WARPS")) { int v = atoi(e); if (v == 8 || v == 12 || v == 16) d->aff_warps = v; }
-    if (const char* e = getenv("RAIKO_KZG_AFFINE_LOCKSTEP")) d->aff_lockstep = atoi(e) != 0;
     d->aff_min_entries = 8 * d->aff_chains;
     if (const char* e = getenv("RAIKO_KZG_AFFINE_MIN_ENTRIES")) d->aff_min_entries = std::max(1, atoi(e));
     if (const char* e = getenv("RAIKO_KZG_MAX_SPLITS_LOG2")) d->max_splits_log2 = std::min(7, std::max(0, atoi(e)));
@@ -406,55 +403,61 @@ struct BatchArgs {
     bool outs_on_device;
 };
 
-int pick_splits_log2(const DeviceCtx* d, size_t nblobs) {
+struct MsmPlan {
+    int splits_log2;
+    bool affine;
+};
+
+MsmPlan plan_msm(const DeviceCtx* d, size_t nblobs) {
     // One warp per (blob, split); every warp of a launch does the same amount of work, so a
-    // launch runs in whole "waves" of sm_count * warps_per_sm warps.  Pick the split that
-    // minimises waves x per-warp work, where a warp costs its lane's additions
-    // (4096 * W / 32 / splits) plus ~8 additions' worth of shuffle-tree reduction.
-    const double slots = (double)d->sm_count * d->warps_per_sm;
+    // launch runs in whole "waves" of resident warps.  Pick the split AND the formulation that
+    // minimise waves x per-warp time.  Per-warp time in units of one XYZZ addition at 8 warps/SM
+    // (measured, profiles/r01/affine_ab_4.txt): k_msm costs its lane's additions plus ~8 for the
+    // shuffle tree; k_msm_affine runs 16 warps/SM, each addition 1.36 units, plus ~150 for the
+    // chain sums and the tree -- so it wins once a lane owns a few hundred table entries.
     const double adds_per_lane = (double)NPTS * d->geom.W / 32.0;
-    int best = 0;
+    MsmPlan best{0, false};
     double best_t = 1e300;
     for (int lg = 0; lg <= d->max_splits_log2; lg++) {
         if ((nblobs << lg) > (size_t)d->max_partials) break;          // one XYZZ partial per warp
         const double warps = (double)(nblobs << lg);
-        const double waves = std::ceil(warps / slots);
-        const double t = waves * (adds_per_lane / (double)(1 << lg) + 8.0);
-        if (t < best_t * 0.999) { best_t = t; best = lg; }
+        const double per_lane = adds_per_lane / (double)(1 << lg);
+        const double t_x = std::ceil(warps / ((double)d->sm_count * d->warps_per_sm)) * (per_lane + 8.0);
+        if (t_x < best_t * 0.999) { best_t = t_x; best = {lg, false}; }
+        const int entries = ((NPTS >> lg) >> 5) * d->geom.W;
+        if (d->msm_affine && d->aff_scratch && entries >= d->aff_min_entries) {
+            const double t_a = std::ceil(warps / ((double)d->sm_count * d->aff_warps)) * (1.36 * per_lane + 150.0);
+            if (t_a < best_t * 0.999) { best_t = t_a; best = {lg, true}; }
+        }
     }
     return best;
 }
 
 void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint32_t* bad, int* splits_out) {
-    MsmParams p;
-    p.table = d->table; p.g = d->geom; p.scalars = scalars; p.nblobs = n;
-    p.splits_log2 = pick_splits_log2(d, (size_t)n);
-    p.partials = s.d_partials; p.bad = bad;
-    const long long warps = (long long)n << p.splits_log2;
-    // entries per lane; the affine kernel needs a few rounds of `chains` entries to pay for its
-    // per-round inversion and the final chain sums
-    const int per_lane_entries = ((NPTS >> p.splits_log2) >> 5) * d->geom.W;
-    const bool affine = d->msm_affine && d->aff_scratch && per_lane_entries >= d->aff_min_entries;
+    const MsmPlan plan = plan_msm(d, (size_t)n);
+    const long long warps = (long long)n << plan.splits_log2;
     timer_begin(d, d->s_main, T_MSM);
-    if (affine) {
+    if (plan.affine) {
         MsmAffParams q;
-        q.table = p.table; q.g = p.g; q.scalars = p.scalars; q.nblobs = n; q.splits_log2 = p.splits_log2;
-        q.partials = p.partials; q.bad = p.bad; q.scratch = d->aff_scratch; q.K = d->aff_chains;
+        q.table = d->table; q.g = d->geom; q.scalars = scalars; q.nblobs = n; q.splits_log2 = plan.splits_log2;
+        q.partials = s.d_partials; q.bad = bad; q.scratch = d->aff_scratch; q.K = d->aff_chains;
         const int wpc = d->aff_warps, threads = 32 * wpc;
         q.ngroups = (int)((warps + wpc - 1) / wpc);
         memcpy(q.H, d->recode_h, sizeof q.H);
         const unsigned grid = (unsigned)std::min<long long>(q.ngroups, d->sm_count);
-        const size_t smem = (size_t)q.K * threads * 4;
-        if (wpc == 8) launch_k_msm_affine(grid, threads, smem, d->s_main, q);
-        else if (wpc == 12) launch_k_msm_affine_w12(grid, threads, smem, d->s_main, q);
-        else if (d->aff_lockstep) launch_k_msm_affine_w16(grid, threads, smem, d->s_main, q);
-        else launch_k_msm_affine_w16n(grid, threads, smem, d->s_main, q);
+        launch_k_msm_affine(grid, threads, (size_t)q.K * threads * 4, d->s_main, q);
+        d->stats.msm_affine_launches++;
+        d->stats.msm_affine_point_adds += (uint64_t)n * NPTS * d->geom.W;
     } else {
+        MsmParams p;
+        p.table = d->table; p.g = d->geom; p.scalars = scalars; p.nblobs = n;
+        p.splits_log2 = plan.splits_log2;
+        p.partials = s.d_partials; p.bad = bad;
         launch_k_msm((unsigned)((warps + 7) / 8), 256, 0, d->s_main, p);
     }
     timer_end(d, d->s_main);
     d->stats.msm_point_adds += (uint64_t)n * NPTS * d->geom.W;
-    *splits_out = 1 << p.splits_log2;
+    *splits_out = 1 << plan.splits_log2;
 }
 
 rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
@@ -1207,6 +1210,7 @@ void rk_kzg_stats_get(rk_kzg_ctx* ctx, rk_kzg_stats* out) {
         out->finalize_ms += d->stats.finalize_ms; out->msm_launches += d->stats.msm_launches;
         out->total_launches += d->stats.total_launches; out->h2d_bytes += d->stats.h2d_bytes;
         out->d2h_bytes += d->stats.d2h_bytes; out->msm_point_adds += d->stats.msm_point_adds;
+        out->msm_affine_launches += d->stats.msm_affine_launches; out->msm_affine_point_adds += d->stats.msm_affine_point_adds;
     }
 }
 

@@ -203,7 +203,7 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
 // can be read at any position without a carry chain; digits of a round are staged in shared
 // memory.  Exceptional additions (equal x: doubling or cancellation) cannot occur between
 // distinct setup points without knowing their discrete logs, but are handled exactly anyway
-// (affine_add_rare), as are empty digits and empty chains.
+// (g1_affine_add_slow), as are empty digits and empty chains.
 // ---------------------------------------------------------------------------
 struct MsmAffParams {
     const TableEntry* table;
@@ -220,23 +220,9 @@ struct MsmAffParams {
 };
 constexpr int AFF_WORDS = 39;   // per chain and thread: x[13] y[13] prefix[13]
 constexpr int MSM_AFF_MAX_K = 64;
+constexpr int MSM_AFF_THREADS = 512;   // 16 warps per SM at 128 registers
 
 #ifdef RK_TU_MSM
-// (x1, y1) += (x2, y2) when x1 == x2 mod p: doubling or cancellation.  Returns false for infinity.
-static __device__ __noinline__ bool affine_add_rare(Fp& x1, Fp& y1, const Fp& x2, const Fp& y2) {
-    G1Xyzz a;
-    fe_set(a.x, x1); fe_set(a.y, y1);
-    fe_const<FpTag, FP_ONE>(a.zz); fe_const<FpTag, FP_ONE>(a.zzz);
-    g1_madd(a, x2, y2);
-    if (g1_is_inf(a)) return false;
-    Fp inv;
-    fe_inv_safegcd(inv, a.zzz);
-    G1Affine r;
-    g1_to_affine_with_inv(r, a, inv);
-    fe_set(x1, r.x); fe_set(y1, r.y);
-    return true;
-}
-
 __device__ __forceinline__ void unpack_entry_x(Fp& x, const uint4 (&t)[3]) {
     uint32_t w[12] = {t[0].x, t[0].y, t[0].z, t[0].w, t[1].x, t[1].y, t[1].z, t[1].w, t[2].x, t[2].y, t[2].z, t[2].w};
     fe_unpack<FpTag>(x, w);
@@ -275,6 +261,21 @@ __device__ __forceinline__ void raw_to_fp(Fp& a, const FpRaw& r) {
 #pragma unroll
     for (int i = 0; i < 3; i++) { a.v[4 * i] = r.q[i].x; a.v[4 * i + 1] = r.q[i].y; a.v[4 * i + 2] = r.q[i].z; a.v[4 * i + 3] = r.q[i].w; }
     a.v[12] = r.top;
+}
+
+// Lockstep barrier of the affine kernel.  SYNC = 0: none; 1: whole CTA; G > 1: the CTA's warps
+// form G independent groups (named barriers 1..G), so the groups drift apart and one group's
+// multiply-heavy phase overlaps another's carry-handling phase while each group still shares
+// its instruction fetches.
+template <int THREADS, int SYNC>
+__device__ __forceinline__ void lockstep() {
+    if constexpr (SYNC == 1) __syncthreads();
+    else if constexpr (SYNC > 1) {
+        constexpr int PER = THREADS / SYNC;
+        const int id = 1 + (int)(threadIdx.x / PER);
+        const int cnt = PER;
+        asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(cnt) : "memory");
+    }
 }
 
 template <int THREADS, int SYNC>
@@ -356,7 +357,7 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
             fe_const<FpTag, FP_ONE>(P);
             unsigned long long act = 0;
             for (int k = 0; k < K; k++) {
-                if (SYNC) __syncthreads();
+                lockstep<THREADS, SYNC>();
                 const uint32_t code = sh_code[k * THREADS + tid];
                 if (!code) continue;
                 const ChainScratch<THREADS> cs(scr, k, tid);
@@ -393,7 +394,7 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
                         chain_load<THREADS>(yr, cs, 1);
                         Fp y1;
                         raw_to_fp(y1, yr);
-                        keep = affine_add_rare(x1, y1, x2, y2);
+                        keep = g1_affine_add_slow(x1, y1, x2, y2);
                         fe_set(x2, x1); fe_set(y2, y1);
                     }
                     if (keep) { chain_store<THREADS>(cs, 0, x2); chain_store<THREADS>(cs, 1, y2); has |= 1ull << k; }
@@ -413,7 +414,7 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
             // ---- backward: peel the inverses off, finish the additions ----------------------
             // Operands are re-read from the scratch (L1/L2 hits) where that shortens a live range.
             for (int k = K - 1; k >= 0; k--) {
-                if (SYNC) __syncthreads();
+                lockstep<THREADS, SYNC>();
                 if (!((act >> k) & 1ull)) continue;
                 const uint32_t code = sh_code[k * THREADS + tid];
                 const ChainScratch<THREADS> cs(scr, k, tid);
@@ -476,7 +477,7 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
         G1Xyzz acc;
         g1_set_inf(acc);
         for (int k = 0; k < K; k++) {
-            if (SYNC) __syncthreads();
+            lockstep<THREADS, SYNC>();
             if (!((has >> k) & 1ull)) continue;
             const ChainScratch<THREADS> cs(scr, k, tid);
             FpRaw xr, yr;
@@ -498,10 +499,14 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
     }
 }
 
-__global__ void __maxnreg__(248) k_msm_affine(MsmAffParams prm) { msm_affine_body<256, 1>(prm); }
-__global__ void __maxnreg__(168) k_msm_affine_w12(MsmAffParams prm) { msm_affine_body<384, 1>(prm); }
-__global__ void __maxnreg__(128) k_msm_affine_w16(MsmAffParams prm) { msm_affine_body<512, 1>(prm); }
-__global__ void __maxnreg__(128) k_msm_affine_w16n(MsmAffParams prm) { msm_affine_body<512, 0>(prm); }
+// Measured on B200, c = 15, 4736 blobs per launch (profiles/r01/affine_ab_*.txt), G additions/s:
+//   XYZZ k_msm 2.35 | this kernel with software prefetch, 8 warps x 248 registers 2.78 |
+//   no prefetch: 8 warps 2.71, 12 warps x 168 registers 2.89, 16 warps x 128 registers 2.94 |
+//   16 warps, no barrier 2.82 | 16 warps in 2 lockstep groups 3.22 | 4 groups 3.18.
+// The kernel is latency-bound (two warps per scheduler left the multiply pipe 64 % busy), so
+// registers are spent on resident warps rather than load buffers, and the two lockstep groups
+// drift apart so one group's multiply phase overlaps the other's carry/ALU phase.
+__global__ void __maxnreg__(128) k_msm_affine(MsmAffParams prm) { msm_affine_body<MSM_AFF_THREADS, 2>(prm); }
 #endif  // RK_TU_MSM (affine)
 
 #ifdef RK_TU_MSM

@@ -4,10 +4,6 @@
 namespace rk {
 RK_KERNELS_MSM(RK_DEFINE_LAUNCH)
 cudaError_t configure_k_msm_affine() {
-    cudaError_t e = cudaFuncSetAttribute(k_msm_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 256 * 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_msm_affine_w12, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 384 * 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_msm_affine_w16, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 512 * 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_msm_affine_w16n, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * 512 * 4);
-    return e;
+    return cudaFuncSetAttribute(k_msm_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * MSM_AFF_THREADS * 4);
 }
 }  // namespace rk

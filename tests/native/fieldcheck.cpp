@@ -39,6 +39,36 @@ int fc_g1_madd(const uint8_t* a, const uint8_t* b, uint8_t* out) {
     G1Xyzz p; G1Affine q; if (load(p, a)) return -1; if (g1_decompress(q, b)) return -1;
     g1_madd(p, q.x, q.y); g1_compress(out, p); return 0; }
 int fc_g1_dbl(const uint8_t* a, uint8_t* out) { G1Xyzz p, r; if (load(p, a)) return -1; g1_dbl(r, p); g1_compress(out, r); return 0; }
+// the batched-affine MSM's pieces: the slow-path addition, and one batch of affine additions
+// sharing one safegcd inversion exactly as k_msm_affine's forward / backward passes do
+// (acc[i] += pts[i], all distinct x), n <= 64
+int fc_g1_affine_add_slow(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    G1Affine p, q; if (g1_decompress(p, a) || g1_decompress(q, b)) return -1;
+    if (!g1_affine_add_slow(p.x, p.y, q.x, q.y)) { g1_compress_inf(out); return 0; }
+    g1_compress_affine(out, p); return 0; }
+int fc_g1_affine_batch_add(const uint8_t* accs, const uint8_t* pts, int n, uint8_t* out) {
+    G1Affine A[64], B[64]; Fp pre[64];
+    if (n > 64) return -1;
+    for (int i = 0; i < n; i++) if (g1_decompress(A[i], accs + 48 * i) || g1_decompress(B[i], pts + 48 * i)) return -1;
+    Fp P; fe_const<FpTag, FP_ONE>(P);
+    for (int k = 0; k < n; k++) { Fp d; fe_sub<FpTag, 2>(d, B[k].x, A[k].x); if (fe_is_zero_mod(d)) return -2; pre[k] = P; fe_mul(P, P, d); }
+    Fp I; fe_inv_safegcd(I, P);
+    for (int k = n - 1; k >= 0; k--) {
+        Fp inv, d, lam, t, u;
+        fe_mul(inv, I, pre[k]);
+        fe_sub<FpTag, 2>(d, B[k].x, A[k].x); fe_mul(I, I, d);
+        fe_add(u, A[k].x, B[k].x);
+        fe_sub<FpTag, 2>(t, B[k].y, A[k].y);
+        fe_mul(lam, t, inv);
+        fe_sqr(t, lam);
+        fe_sub<FpTag, 3>(t, t, u); fe_reduce_loose<FpTag>(t);
+        fe_sub<FpTag, 2>(u, A[k].x, t); fe_mul(u, lam, u);
+        fe_sub<FpTag, 2>(u, u, A[k].y); fe_reduce_loose<FpTag>(u);
+        A[k].x = t; A[k].y = u;
+        g1_compress_affine(out + 48 * k, A[k]);
+    }
+    return 0; }
+void fc_fp_reduce_loose(const uint32_t* a, uint32_t* r) { Fp x; memcpy(x.v, a, 52); fe_reduce_loose<FpTag>(x); memcpy(r, x.v, 52); }
 // k*P by double-and-add through madd/dbl (exercises long chains with loose bounds)
 int fc_g1_mul_u64(const uint8_t* a, uint64_t k, uint8_t* out) {
     G1Affine q; if (g1_decompress(q, a)) return -1;

@@ -118,3 +118,61 @@ def test_g1_formulas_and_exceptional_cases(L, pyoracle):
     allpts = b"".join(o.g1_compress(p) for p in s.g1)
     out = buf()
     assert L.fc_g1_sum(allpts, 4096, out) == 0 and out.raw == o.g1_compress(o.G1_GEN)
+
+
+@pytest.mark.parametrize("name,mod,n", [("fp", P, 13), ("fr", R, 9)])
+def test_safegcd_inversion(L, name, mod, n):
+    """fe_inv_safegcd (Bernstein-Yang division steps on signed 30-bit limbs): Montgomery in,
+    Montgomery out, fully reduced; inputs anywhere below 8 mod."""
+    rnd = random.Random(31 + n)
+    MR = 1 << (30 * n)
+    fn = getattr(L, "fc_%s_inv_safegcd" % name)
+    cases = [1, 2, mod - 1, mod + 1, 2 * mod - 1, 8 * mod - 1, MR % mod, (1 << 200) + 1] + [rnd.randrange(1, 8 * mod) for _ in range(4000)]
+    for x in cases:
+        if x % mod == 0:
+            continue
+        out = (ctypes.c_uint32 * n)()
+        fn(limbs(x, n), out)
+        r = val(out)
+        assert r < mod and all(v < (1 << 30) for v in out)
+        assert r == MR * MR * pow(x, -1, mod) % mod                       # x = aR  ->  a^-1 R
+    out = (ctypes.c_uint32 * n)()
+    fn(limbs(0, n), out)
+    assert val(out) == 0
+
+
+def test_reduce_loose(L):
+    rnd = random.Random(77)
+    top = P >> 360
+    for t in range(5000):
+        a = (1 << 390) - 1 if t == 0 else rnd.randrange(8 * P) if t % 2 else rnd.randrange(1 << 390)
+        out = (ctypes.c_uint32 * 13)()
+        L.fc_fp_reduce_loose(limbs(a, 13), out)
+        r = val(out)
+        q = (a >> 360) // (top + 1)
+        assert r == a - q * P and 0 <= r < P + ((q + 2) << 360) and all(v < (1 << 30) for v in out[:12])
+        if a < 8 * P:
+            assert r < P * 1.0001
+
+
+def test_affine_batch_addition_pieces(L, pyoracle):
+    """The two halves of k_msm_affine's arithmetic on the host: one batch of affine additions
+    under a shared safegcd inversion (forward prefix products, backward peel), and the slow path
+    for equal x (doubling, cancellation)."""
+    o, _ = pyoracle
+    rnd = random.Random(11)
+    n = 24
+    accs = [o.g1_mul(o.G1_GEN, rnd.randrange(1, R)) for _ in range(n)]
+    pts = [o.g1_mul(o.G1_GEN, rnd.randrange(1, R)) for _ in range(n)]
+    out = ctypes.create_string_buffer(48 * n)
+    rc = L.fc_g1_affine_batch_add(b"".join(map(o.g1_compress, accs)), b"".join(map(o.g1_compress, pts)), n, out)
+    assert rc == 0
+    for i in range(n):
+        assert out.raw[48 * i:48 * i + 48] == o.g1_compress(o.g1_add(accs[i], pts[i])), i
+    # equal x is refused by the batch and done by the slow path
+    assert L.fc_g1_affine_batch_add(o.g1_compress(accs[0]), o.g1_compress(accs[0]), 1, out) == -2
+    assert L.fc_g1_affine_batch_add(o.g1_compress(accs[0]), o.g1_compress(o.g1_neg(accs[0])), 1, out) == -2
+    one = ctypes.create_string_buffer(48)
+    for a, b in ((accs[0], accs[0]), (accs[1], o.g1_neg(accs[1])), (accs[2], pts[2])):
+        assert L.fc_g1_affine_add_slow(o.g1_compress(a), o.g1_compress(b), one) == 0
+        assert one.raw == o.g1_compress(o.g1_add(a, b))

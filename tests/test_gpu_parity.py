@@ -306,3 +306,88 @@ def test_concurrent_single_blob_calls_are_merged(gpu_settings, golden):
         want = cases[i]["commitment"] if kind == "c" else cases[i]["proofs"][0]["proof"]
         assert val.hex() == want
     print("16 serial commitments %.1f ms; 32 concurrent mixed calls %.1f ms" % (serial * 1e3, merged * 1e3))
+
+
+@pytest.fixture
+def msm_env():
+    """Sets RAIKO_KZG_* knobs (read when a context is created) and restores them afterwards."""
+    saved = {}
+
+    def set_env(**kw):
+        for k, v in kw.items():
+            saved.setdefault(k, os.environ.get(k))
+            os.environ[k] = str(v)
+    yield set_env
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("wb,chains", [(8, 64), (15, 64), (11, 6)])
+def test_affine_msm_kernel_on_every_golden(wb, chains, golden, msm_env):
+    """k_msm_affine (batched affine additions, shared safegcd inversion) forced onto EVERY golden
+    case: one warp per blob, so each lane runs full chains through the zero blob (no entries at
+    all), the sparse blob (one entry), constant blobs (every digit pattern equal), the in-domain
+    evaluation points and the maximal field element.  Small batches normally take the XYZZ
+    kernel; the planner is overridden here.  Also checks both kernels agree on random blobs."""
+    import torch
+    import raiko_b200 as rk
+    if wb == 15 and torch.cuda.mem_get_info()[0] < 130e9:
+        pytest.skip("not enough free HBM for the c=15 table")
+    msm_env(RAIKO_KZG_MSM_AFFINE=1, RAIKO_KZG_AFFINE_MIN_ENTRIES=1, RAIKO_KZG_MAX_SPLITS_LOG2=0, RAIKO_KZG_AFFINE_CHAINS=chains)
+    s = rk.KzgSettings(window_bits=wb)
+    try:
+        cases = golden["cases"]
+        blobs = [blob_from_recipe(c["recipe"]) for c in cases]
+        s.stats_enable(True)
+        s.stats_reset()
+        res = rk.commit_prove_batch(blobs, s)
+        st = s.stats()
+        assert st["msm_affine_launches"] == st["msm_launches"] == 2
+        for i, c in enumerate(cases):
+            p0 = c["proofs"][0]
+            got = (res.commitments[i].hex(), res.versioned_hashes[i].hex(), res.xs[i].hex(), res.ys[i].hex(), res.proofs[i].hex())
+            assert got == (c["commitment"], c["versioned_hash"], p0["z"], p0["y"], p0["proof"]), c["name"]
+            assert res.status[i] == 0
+        for c in cases:                                   # every (z, y, proof) incl. z inside the domain
+            blob = blob_from_recipe(c["recipe"])
+            zs = [bytes.fromhex(p["z"]) for p in c["proofs"]]
+            r = rk.compute_kzg_proof_batch([blob] * len(zs), zs, s)
+            assert [x.hex() for x in r.proofs] == [p["proof"] for p in c["proofs"]], c["name"]
+        bads = [blob_from_recipe(e["recipe"]) for e in golden["errors"]]     # element 0 / 4095 / 2048 not canonical
+        r = rk.commit_batch([blobs[4]] + bads + [blobs[5]], s)
+        assert r.status == [0] + [2] * len(bads) + [0]
+        assert r.commitments[0].hex() == cases[4]["commitment"] and r.commitments[-1].hex() == cases[5]["commitment"]
+    finally:
+        s.close()
+
+
+def test_affine_and_xyzz_kernels_agree(ref, msm_env):
+    """600 random blobs (enough for the planner to pick k_msm_affine on its own) against the same
+    batch with the affine kernel switched off, and a sample against the C oracle."""
+    import torch
+    import raiko_b200 as rk
+    n = 600
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99)
+    blobs = torch.randint(0, 256, (n, 4096, 32), dtype=torch.uint8, device="cuda", generator=g)
+    blobs[:, :, 0] %= 0x73
+    out = {}
+    for mode in (1, 0):
+        msm_env(RAIKO_KZG_MSM_AFFINE=mode)
+        s = rk.KzgSettings(window_bits=8)
+        try:
+            s.stats_enable(True)
+            s.stats_reset()
+            out[mode] = rk.commit_prove_batch(blobs, s)
+            st = s.stats()
+            assert (st["msm_affine_launches"] > 0) == (mode == 1)
+        finally:
+            s.close()
+    for f in ("commitments", "versioned_hashes", "xs", "ys", "proofs", "status"):
+        assert getattr(out[0], f) == getattr(out[1], f), f
+    for i in (0, 299, 599):
+        want = ref.commit_prove(blobs[i].cpu().numpy().tobytes())
+        assert (out[1].commitments[i], out[1].versioned_hashes[i], out[1].xs[i], out[1].ys[i], out[1].proofs[i]) == want
