@@ -108,8 +108,9 @@ struct DeviceCtx {
     // RAIKO_KZG_SHA_SERIAL=0) its latency-bound warps sit in the MSM's issue slots and cost the
     // MSM 3-6 %, more than the 3.3 ms per chunk the hash takes alone.
     bool sha_serial = true;
-    // MSM formulation: 1 = batched affine additions (k_msm_affine) for launches whose lanes own
-    // enough table entries to fill the chains, 0 = XYZZ only (k_msm).  RAIKO_KZG_MSM_AFFINE.
+    // MSM formulation (RAIKO_KZG_MSM_AFFINE): 1 = batched affine additions (k_msm_affine) where the
+    // planner estimates them faster, i.e. launches whose lanes own a few hundred table entries;
+    // 0 = XYZZ only (k_msm); 2 = affine wherever eligible (tests).
     int msm_affine = 1;
     int aff_chains = MSM_AFF_MAX_K;
     int aff_warps = MSM_AFF_THREADS / 32;      // warps per CTA of the affine kernel (one CTA per SM)
@@ -423,9 +424,10 @@ MsmPlan plan_msm(const DeviceCtx* d, size_t nblobs) {
         const double warps = (double)(nblobs << lg);
         const double per_lane = adds_per_lane / (double)(1 << lg);
         const double t_x = std::ceil(warps / ((double)d->sm_count * d->warps_per_sm)) * (per_lane + 8.0);
-        if (t_x < best_t * 0.999) { best_t = t_x; best = {lg, false}; }
         const int entries = ((NPTS >> lg) >> 5) * d->geom.W;
-        if (d->msm_affine && d->aff_scratch && entries >= d->aff_min_entries) {
+        const bool eligible = d->msm_affine && d->aff_scratch && entries >= d->aff_min_entries;
+        if (!(eligible && d->msm_affine == 2) && t_x < best_t * 0.999) { best_t = t_x; best = {lg, false}; }
+        if (eligible) {
             const double t_a = std::ceil(warps / ((double)d->sm_count * d->aff_warps)) * (1.36 * per_lane + 150.0);
             if (t_a < best_t * 0.999) { best_t = t_a; best = {lg, true}; }
         }

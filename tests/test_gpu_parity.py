@@ -336,7 +336,7 @@ def test_affine_msm_kernel_on_every_golden(wb, chains, golden, msm_env):
     import raiko_b200 as rk
     if wb == 15 and torch.cuda.mem_get_info()[0] < 130e9:
         pytest.skip("not enough free HBM for the c=15 table")
-    msm_env(RAIKO_KZG_MSM_AFFINE=1, RAIKO_KZG_AFFINE_MIN_ENTRIES=1, RAIKO_KZG_MAX_SPLITS_LOG2=0, RAIKO_KZG_AFFINE_CHAINS=chains)
+    msm_env(RAIKO_KZG_MSM_AFFINE=2, RAIKO_KZG_AFFINE_MIN_ENTRIES=1, RAIKO_KZG_MAX_SPLITS_LOG2=0, RAIKO_KZG_AFFINE_CHAINS=chains)
     s = rk.KzgSettings(window_bits=wb)
     try:
         cases = golden["cases"]
@@ -365,11 +365,12 @@ def test_affine_msm_kernel_on_every_golden(wb, chains, golden, msm_env):
 
 
 def test_affine_and_xyzz_kernels_agree(ref, msm_env):
-    """600 random blobs (enough for the planner to pick k_msm_affine on its own) against the same
-    batch with the affine kernel switched off, and a sample against the C oracle."""
+    """2368 random blobs (one full wave of the affine kernel: the planner picks k_msm_affine on its
+    own) against the same batch with the affine kernel switched off, and a sample against the C
+    oracle."""
     import torch
     import raiko_b200 as rk
-    n = 600
+    n = 2368
     g = torch.Generator(device="cuda")
     g.manual_seed(99)
     blobs = torch.randint(0, 256, (n, 4096, 32), dtype=torch.uint8, device="cuda", generator=g)
@@ -388,6 +389,6 @@ def test_affine_and_xyzz_kernels_agree(ref, msm_env):
             s.close()
     for f in ("commitments", "versioned_hashes", "xs", "ys", "proofs", "status"):
         assert getattr(out[0], f) == getattr(out[1], f), f
-    for i in (0, 299, 599):
+    for i in (0, 1183, n - 1):
         want = ref.commit_prove(blobs[i].cpu().numpy().tobytes())
         assert (out[1].commitments[i], out[1].versioned_hashes[i], out[1].xs[i], out[1].ys[i], out[1].proofs[i]) == want
