@@ -395,16 +395,20 @@ RK_HD void fe_inv_safegcd(Fe<F>& out, const Fe<F>& a) {
 #pragma unroll
         for (int i = 0; i < N; i++) nz |= (uint32_t)g[i];
         if (nz == 0) break;
-        // ---- 30 division steps on the low words; (u v; q r) accumulates the transition matrix
+        // ---- 30 division steps on the low words; (u v; q r) accumulates the transition matrix.
+        // Stated with multiplies by -1/0/+1 instead of mask-and-add: one IMAD replaces the
+        // xor / sub / and / add of a conditional signed accumulation (17 instructions per step
+        // instead of 27).
         uint32_t u = 1, v = 0, q = 0, r = 1, fl = (uint32_t)f[0] | ((uint32_t)f[1] << 30), gl = (uint32_t)g[0] | ((uint32_t)g[1] << 30);
 #pragma unroll 6
         for (int s = 0; s < 30; s++) {
-            uint32_t m1 = (uint32_t)(zeta >> 31), m2 = 0u - (gl & 1u);
-            uint32_t x = (fl ^ m1) - m1, y = (u ^ m1) - m1, z = (v ^ m1) - m1;
-            gl += x & m2; q += y & m2; r += z & m2;
-            m1 &= m2;
-            zeta = (int32_t)((uint32_t)zeta ^ m1) - 1;
-            fl += gl & m1; u += q & m1; v += r & m1;
+            const uint32_t odd = gl & 1u;                          // g odd?
+            const uint32_t neg = (uint32_t)zeta >> 31;             // zeta < 0  (delta > 0)?
+            const uint32_t sw = odd & neg;                         // swap step
+            const uint32_t sg = odd - 2u * sw;                     // +1: g += f, -1 (as 2^32-1): g -= f, 0: g even
+            gl += fl * sg; q += u * sg; r += v * sg;               // (g, q, r) += sg * (f, u, v)
+            zeta = (int32_t)(((uint32_t)zeta ^ (0u - sw)) - 1u);   // swap: -zeta - 2, else zeta - 1
+            fl += gl * sw; u += q * sw; v += r * sw;               // swap: (f, u, v) += new (g, q, r)
             gl >>= 1; u <<= 1; v <<= 1;
         }
         const int32_t U = (int32_t)u, V = (int32_t)v, Q = (int32_t)q, Rr = (int32_t)r;
@@ -412,8 +416,10 @@ RK_HD void fe_inv_safegcd(Fe<F>& out, const Fe<F>& a) {
         {
             const int32_t sd = d[N - 1] >> 31, se = e[N - 1] >> 31;
             int32_t md = (U & sd) + (V & se), me = (Q & sd) + (Rr & se);
-            int64_t cd = (int64_t)U * d[0] + (int64_t)V * e[0];
-            int64_t ce = (int64_t)Q * d[0] + (int64_t)Rr * e[0];
+            int64_t cd = (int64_t)U * d[0];
+            cd += (int64_t)V * e[0];
+            int64_t ce = (int64_t)Q * d[0];
+            ce += (int64_t)Rr * e[0];
             md -= (int32_t)((F::MINV * (uint32_t)cd + (uint32_t)md) & LIMB_MASK);
             me -= (int32_t)((F::MINV * (uint32_t)ce + (uint32_t)me) & LIMB_MASK);
             cd += (int64_t)(int32_t)F::MOD::at(0) * md;
@@ -421,8 +427,13 @@ RK_HD void fe_inv_safegcd(Fe<F>& out, const Fe<F>& a) {
             cd >>= 30; ce >>= 30;
 #pragma unroll
             for (int i = 1; i < N; i++) {
-                cd += (int64_t)U * d[i] + (int64_t)V * e[i] + (int64_t)(int32_t)F::MOD::at(i) * md;
-                ce += (int64_t)Q * d[i] + (int64_t)Rr * e[i] + (int64_t)(int32_t)F::MOD::at(i) * me;
+                // one multiply-accumulate per statement: each becomes a single IMAD.WIDE
+                cd += (int64_t)U * d[i];
+                cd += (int64_t)V * e[i];
+                cd += (int64_t)(int32_t)F::MOD::at(i) * md;
+                ce += (int64_t)Q * d[i];
+                ce += (int64_t)Rr * e[i];
+                ce += (int64_t)(int32_t)F::MOD::at(i) * me;
                 d[i - 1] = (int32_t)cd & M30; cd >>= 30;
                 e[i - 1] = (int32_t)ce & M30; ce >>= 30;
             }
@@ -430,13 +441,17 @@ RK_HD void fe_inv_safegcd(Fe<F>& out, const Fe<F>& a) {
         }
         // ---- (f, g) <- (U f + V g, Q f + R g) / 2^30  (exact)
         {
-            int64_t cf = (int64_t)U * f[0] + (int64_t)V * g[0];
-            int64_t cg = (int64_t)Q * f[0] + (int64_t)Rr * g[0];
+            int64_t cf = (int64_t)U * f[0];
+            cf += (int64_t)V * g[0];
+            int64_t cg = (int64_t)Q * f[0];
+            cg += (int64_t)Rr * g[0];
             cf >>= 30; cg >>= 30;
 #pragma unroll
             for (int i = 1; i < N; i++) {
-                cf += (int64_t)U * f[i] + (int64_t)V * g[i];
-                cg += (int64_t)Q * f[i] + (int64_t)Rr * g[i];
+                cf += (int64_t)U * f[i];
+                cf += (int64_t)V * g[i];
+                cg += (int64_t)Q * f[i];
+                cg += (int64_t)Rr * g[i];
                 f[i - 1] = (int32_t)cf & M30; cf >>= 30;
                 g[i - 1] = (int32_t)cg & M30; cg >>= 30;
             }

@@ -14,6 +14,9 @@ from kzg_testlib import SETUP
 wb = int(sys.argv[1]) if len(sys.argv) > 1 else 15
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4736
 chains = [a for a in sys.argv[3:]] or ["64"]     # "chains" or "chains:warps"
+if os.environ.get("RAIKO_KZG_LIB_OVERRIDE"):      # A/B of differently compiled libraries (e.g. -DRK_MAC_FORM=1)
+    _native.LIB_PATH = os.path.abspath(os.environ["RAIKO_KZG_LIB_OVERRIDE"])
+    print("library:", _native.LIB_PATH)
 lib = _native.load()
 g = torch.Generator(device="cuda"); g.manual_seed(7)
 blobs = torch.randint(0, 256, (n, 4096, 32), dtype=torch.uint8, device="cuda", generator=g)
