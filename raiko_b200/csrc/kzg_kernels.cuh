@@ -502,7 +502,9 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
 // Measured on B200, c = 15, 4736 blobs per launch (profiles/r01/affine_ab_*.txt), G additions/s:
 //   XYZZ k_msm 2.35 | this kernel with software prefetch, 8 warps x 248 registers 2.78 |
 //   no prefetch: 8 warps 2.71, 12 warps x 168 registers 2.89, 16 warps x 128 registers 2.94 |
-//   16 warps, no barrier 2.82 | 16 warps in 2 lockstep groups 3.22 | 4 groups 3.18.
+//   16 warps, no barrier 2.82 | 16 warps in 2 lockstep groups 3.22 | 4 groups 3.18 |
+//   2 groups + prefetch.global.L2 of the next step's table entry 3.06, of its chain state too 3.08
+//   (against 3.29 without, after the inversion was trimmed): hints cost more than they hide.
 // The kernel is latency-bound (two warps per scheduler left the multiply pipe 64 % busy), so
 // registers are spent on resident warps rather than load buffers, and the two lockstep groups
 // drift apart so one group's multiply phase overlaps the other's carry/ALU phase.
