@@ -361,9 +361,10 @@ RK_HD_NOINLINE void fe_pow_const(Fe<F>& r, const Fe<F>& a) {
     fe_set<F>(r, acc);
 }
 
-// Fermat inversion (0 -> 0).  Input < 8 mod, output < 1.11 mod.
+// Fermat inversion (0 -> 0).  Input < 8 mod, output < 1.11 mod.  Kept as the independent
+// cross-check of fe_inv_safegcd in the host tests; the product paths use fe_inv below.
 template <class F>
-RK_HD void fe_inv(Fe<F>& r, const Fe<F>& a) {
+RK_HD void fe_inv_fermat(Fe<F>& r, const Fe<F>& a) {
     fe_pow_const<F, typename F::EXP_INV, F::W32>(r, a);
 }
 
@@ -379,8 +380,7 @@ RK_HD void fe_inv(Fe<F>& r, const Fe<F>& a) {
 //
 // Input: Montgomery form, < 8 mod, normalised limbs, != 0 mod p.  Output: Montgomery form of
 // the inverse, fully reduced to [0, mod).  (d, e) start as (0, R^2), so the Montgomery
-// factors cancel: (aR)^-1 * R^2 = a^-1 R.  Zero returns 0; other multiples of the modulus have no
-// inverse and return an unspecified value (callers exclude them).
+// factors cancel: (aR)^-1 * R^2 = a^-1 R.  Any multiple of the modulus (zero included) returns 0.
 // ---------------------------------------------------------------------------
 template <class F>
 RK_HD void fe_inv_safegcd(Fe<F>& out, const Fe<F>& a) {
@@ -458,8 +458,20 @@ RK_HD void fe_inv_safegcd(Fe<F>& out, const Fe<F>& a) {
             f[N - 1] = (int32_t)cf; g[N - 1] = (int32_t)cg;
         }
     }
-    // f = +-1 now; result = sign(f) * d, brought from (-2 mod, mod) into [0, mod)
+    // f = +-gcd(a, mod) now: +-1 unless a was a multiple of the modulus, which maps to 0 like the
+    // Fermat ladder's a^(mod-2).  Result = sign(f) * d, brought from (-2 mod, mod) into [0, mod).
     const int32_t neg = f[N - 1] >> 31;
+    {
+        // +1 = (1, 0, ..., 0);  -1 = (2^30-1, ..., 2^30-1, -1) with the signed top limb
+        uint32_t dev = (uint32_t)f[0] ^ (neg ? LIMB_MASK : 1u);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) dev |= (uint32_t)f[i] ^ ((uint32_t)neg & LIMB_MASK);
+        dev |= (uint32_t)f[N - 1] ^ (uint32_t)neg;
+        if (dev != 0) {
+#pragma unroll
+            for (int i = 0; i < N; i++) d[i] = 0;
+        }
+    }
     int32_t add = d[N - 1] >> 31, carry = 0;
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -477,5 +489,9 @@ RK_HD void fe_inv_safegcd(Fe<F>& out, const Fe<F>& a) {
         out.v[i] = (uint32_t)t;
     }
 }
+
+// Field inversion as the rest of the code calls it (0 -> 0).  Input < 8 mod, output in [0, mod).
+template <class F>
+RK_HD void fe_inv(Fe<F>& r, const Fe<F>& a) { fe_inv_safegcd<F>(r, a); }
 
 }  // namespace rk

@@ -19,8 +19,8 @@ void fc_fp_unpack(const uint32_t* w, uint32_t* a) { Fp x; fe_unpack<FpTag>(x, w)
 void fc_fr_pack(const uint32_t* a, uint32_t* w) { Fr x; memcpy(x.v, a, 36); fe_pack<FrTag>(w, x); }
 void fc_fr_unpack(const uint32_t* w, uint32_t* a) { Fr x; fe_unpack<FrTag>(x, w); memcpy(a, x.v, 36); }
 // canonical words in, canonical words out
-void fc_fp_inv(const uint32_t* w, uint32_t* out) { Fp x, m, i, c; fe_unpack<FpTag>(x, w); fe_to_mont(m, x); fe_inv(i, m); fe_from_mont(c, i); fe_pack<FpTag>(out, c); }
-void fc_fr_inv(const uint32_t* w, uint32_t* out) { Fr x, m, i, c; fe_unpack<FrTag>(x, w); fe_to_mont(m, x); fe_inv(i, m); fe_from_mont(c, i); fe_pack<FrTag>(out, c); }
+void fc_fp_inv(const uint32_t* w, uint32_t* out) { Fp x, m, i, c; fe_unpack<FpTag>(x, w); fe_to_mont(m, x); fe_inv_fermat(i, m); fe_from_mont(c, i); fe_pack<FpTag>(out, c); }
+void fc_fr_inv(const uint32_t* w, uint32_t* out) { Fr x, m, i, c; fe_unpack<FrTag>(x, w); fe_to_mont(m, x); fe_inv_fermat(i, m); fe_from_mont(c, i); fe_pack<FrTag>(out, c); }
 
 // safegcd inversion: raw Montgomery limbs in (< 8 mod), raw Montgomery limbs out
 void fc_fp_inv_safegcd(const uint32_t* a, uint32_t* r) { Fp x, z; memcpy(x.v, a, 52); fe_inv_safegcd(z, x); memcpy(r, z.v, 52); }

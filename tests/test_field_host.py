@@ -136,9 +136,10 @@ def test_safegcd_inversion(L, name, mod, n):
         r = val(out)
         assert r < mod and all(v < (1 << 30) for v in out)
         assert r == MR * MR * pow(x, -1, mod) % mod                       # x = aR  ->  a^-1 R
-    out = (ctypes.c_uint32 * n)()
-    fn(limbs(0, n), out)
-    assert val(out) == 0
+    for k in range(8):                                                     # multiples of the modulus -> 0, like a^(mod-2)
+        out = (ctypes.c_uint32 * n)()
+        fn(limbs(k * mod, n), out)
+        assert val(out) == 0
 
 
 def test_reduce_loose(L):
