@@ -203,7 +203,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -397,10 +397,32 @@ def run_ours(args):
         "kernel_ms": {k: stats[k] for k in ("msm_ms", "fr_ms", "sha_ms", "finalize_ms")},
         "host_wall_ms_per_step": 1e3 * (w1 - w0) / args.steps, "parity_checked_blobs": parity_n,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The ONE JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
+def quiet_stdout():
+    """Libraries print to stdout too (NCCL's version banner, for one).  Everything except the
+    JSON line goes to stderr: fd 1 is pointed at fd 2 and the line is written to the saved fd."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
@@ -410,6 +432,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
