@@ -534,6 +534,9 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
 //   16 warps, no barrier 2.82 | 16 warps in 2 lockstep groups 3.22 | 4 groups 3.18 |
 //   2 groups + prefetch.global.L2 of the next step's table entry 3.06, of its chain state too 3.08
 //   (against 3.29 without, after the inversion was trimmed): hints cost more than they hide.
+//   Also tried, no measurable change (+-1 % run to run): the loose reductions' q * p rows from a
+//   shared-memory table instead of 64-bit multiply-subtracts (3.25 / 3.30); and for the XYZZ
+//   kernel, which is pipe-bound, two lockstep groups of 4 warps (2.34 vs 2.35).
 // The kernel is latency-bound (two warps per scheduler left the multiply pipe 64 % busy), so
 // registers are spent on resident warps rather than load buffers, and the two lockstep groups
 // drift apart so one group's multiply phase overlaps the other's carry/ALU phase.
