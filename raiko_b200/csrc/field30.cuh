@@ -208,18 +208,6 @@ RK_HD void fe_sub(Fe<F>& r, const Fe<F>& a, const Fe<F>& b) {
     }
 }
 
-// r = a - b - c + K*mod in one carry pass  (caller guarantees b + c <= K*mod)
-template <class F, int K>
-RK_HD void fe_sub2(Fe<F>& r, const Fe<F>& a, const Fe<F>& b, const Fe<F>& c) {
-    int32_t carry = 0;
-#pragma unroll
-    for (int i = 0; i < F::N; i++) {
-        int32_t t = (int32_t)(a.v[i] + F::modx(K, i)) - (int32_t)b.v[i] - (int32_t)c.v[i] + carry;
-        carry = t >> LIMB_BITS;                 // arithmetic shift: -2 .. 1
-        r.v[i] = launder((uint32_t)t & LIMB_MASK);
-    }
-}
-
 // r = K*mod - a
 template <class F, int K>
 RK_HD void fe_neg(Fe<F>& r, const Fe<F>& a) {

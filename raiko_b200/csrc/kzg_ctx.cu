@@ -446,10 +446,8 @@ void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint3
         const int wpc = d->aff_warps, threads = 32 * wpc;
         q.ngroups = (int)((warps + wpc - 1) / wpc);
         memcpy(q.H, d->recode_h, sizeof q.H);
-        for (int m = 0; m < 8; m++)
-            for (int i = 0; i < FP_N; i++) q.pmul[m * FP_N + i] = m == 0 ? 0u : FpTag::modx(m, i);
         const unsigned grid = (unsigned)std::min<long long>(q.ngroups, d->sm_count);
-        launch_k_msm_affine(grid, threads, ((size_t)q.K * threads + PMUL_WORDS) * 4, d->s_main, q);
+        launch_k_msm_affine(grid, threads, (size_t)q.K * threads * 4, d->s_main, q);
         d->stats.msm_affine_launches++;
         d->stats.msm_affine_point_adds += (uint64_t)n * NPTS * d->geom.W;
     } else {
@@ -457,8 +455,7 @@ void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint3
         p.table = d->table; p.g = d->geom; p.scalars = scalars; p.nblobs = n;
         p.splits_log2 = plan.splits_log2;
         p.partials = s.d_partials; p.bad = bad;
-        if (getenv("RAIKO_KZG_XYZZ_GROUPS")) launch_k_msm_g2((unsigned)((warps + 7) / 8), 256, 0, d->s_main, p);
-        else launch_k_msm((unsigned)((warps + 7) / 8), 256, 0, d->s_main, p);
+        launch_k_msm((unsigned)((warps + 7) / 8), 256, 0, d->s_main, p);
     }
     timer_end(d, d->s_main);
     d->stats.msm_point_adds += (uint64_t)n * NPTS * d->geom.W;

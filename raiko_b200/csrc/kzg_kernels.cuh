@@ -87,22 +87,7 @@ __device__ __forceinline__ void load_scalar_be(uint32_t (&s)[8], const uint8_t* 
 }
 
 #ifdef RK_TU_MSM
-// Lockstep barrier of the MSM kernels.  SYNC = 0: none; 1: whole CTA; G > 1: the CTA's warps
-// form G independent groups (named barriers 1..G), so the groups drift apart and one group's
-// multiply-heavy phase overlaps another's carry-handling phase while each group still shares
-// its instruction fetches.
-template <int THREADS, int SYNC>
-__device__ __forceinline__ void lockstep() {
-    if constexpr (SYNC == 1) __syncthreads();
-    else if constexpr (SYNC > 1) {
-        constexpr int PER = THREADS / SYNC;
-        const int id = 1 + (int)(threadIdx.x / PER);
-        const int cnt = PER;
-        asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(cnt) : "memory");
-    }
-}
-
-template <int THREADS, int MIN_BLOCKS, int SYNC_EVERY, bool CALLS, int GROUPS = 1>
+template <int THREADS, int MIN_BLOCKS, int SYNC_EVERY, bool CALLS>
 __device__ __forceinline__ void msm_body(const MsmParams& prm) {
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -138,7 +123,7 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
         // Keep the CTA's warps in step: the addition below is ~85 KB of straight-line code, far
         // more than the instruction cache holds, so warps that drift apart each stream it from
         // L2 separately.  In step, one fetch serves all of them.
-        if (SYNC_EVERY > 0 && (it % SYNC_EVERY) == 0) lockstep<THREADS, GROUPS>();
+        if (SYNC_EVERY > 0 && (it % SYNC_EVERY) == 0) __syncthreads();
         if (it < total) {
             if (j == 0) {
                 const int pt = first_pt + 32 * t;
@@ -232,13 +217,10 @@ struct MsmAffParams {
     int K;                    // chains per lane, 1..64
     int ngroups;              // groups of block-size / 32 warps (one CTA pass each)
     uint32_t H[8];            // recoding constant, little-endian words
-    uint32_t pmul[8 * FP_N];  // q * p, q = 0..7, normalised 30-bit limbs (for reduce_loose_tbl)
 };
 constexpr int AFF_WORDS = 39;   // per chain and thread: x[13] y[13] prefix[13]
 constexpr int MSM_AFF_MAX_K = 64;
 constexpr int MSM_AFF_THREADS = 512;   // 16 warps per SM at 128 registers
-constexpr int PMUL_STRIDE = 20;        // shared-memory table of q * p rows (reduce_loose_tbl)
-constexpr int PMUL_WORDS = 8 * PMUL_STRIDE;
 
 #ifdef RK_TU_MSM
 __device__ __forceinline__ void unpack_entry_x(Fp& x, const uint4 (&t)[3]) {
@@ -281,35 +263,24 @@ __device__ __forceinline__ void raw_to_fp(Fp& a, const FpRaw& r) {
     a.v[12] = r.top;
 }
 
-// fe_reduce_loose with the multiples q * p (q = 0..7) read from shared memory instead of being
-// rebuilt with 64-bit multiply-subtracts: rows are 20 words apart so that lanes with different
-// q hit different banks, and a row moves in three 128-bit loads and one word.
-__device__ __forceinline__ void pmul_table_fill(uint32_t* tbl, const uint32_t* pmul /* [8][13] */, int tid) {
-    if (tid < PMUL_WORDS) {
-        const int q = tid / PMUL_STRIDE, i = tid - q * PMUL_STRIDE;
-        tbl[tid] = i < FP_N ? pmul[q * FP_N + i] : 0u;
-    }
-}
-__device__ __forceinline__ void reduce_loose_tbl(Fp& a, const uint32_t* tbl) {
-    const uint32_t q = a.v[FP_N - 1] / (FP_MOD::at(FP_N - 1) + 1u);      // <= 7 for a < 8p
-    const uint4* row = reinterpret_cast<const uint4*>(tbl + q * PMUL_STRIDE);
-    const uint4 r0 = row[0], r1 = row[1], r2 = row[2];
-    const uint32_t m[FP_N] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, tbl[q * PMUL_STRIDE + 12]};
-    int32_t carry = 0;
-#pragma unroll
-    for (int i = 0; i < FP_N; i++) {
-        int32_t t = (int32_t)a.v[i] - (int32_t)m[i] + carry;
-        if (i < FP_N - 1) { carry = t >> LIMB_BITS; a.v[i] = launder((uint32_t)t & LIMB_MASK); }
-        else a.v[i] = (uint32_t)t;
+// Lockstep barrier of the affine kernel.  SYNC = 0: none; 1: whole CTA; G > 1: the CTA's warps
+// form G independent groups (named barriers 1..G), so the groups drift apart and one group's
+// multiply-heavy phase overlaps another's carry-handling phase while each group still shares
+// its instruction fetches.
+template <int THREADS, int SYNC>
+__device__ __forceinline__ void lockstep() {
+    if constexpr (SYNC == 1) __syncthreads();
+    else if constexpr (SYNC > 1) {
+        constexpr int PER = THREADS / SYNC;
+        const int id = 1 + (int)(threadIdx.x / PER);
+        const int cnt = PER;
+        asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(cnt) : "memory");
     }
 }
 
 template <int THREADS, int SYNC>
 __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
     extern __shared__ uint32_t sh_code[];          // [K][THREADS]: table entry index + 1, bit 31 = negate; 0 = no entry
-    uint32_t* const sh_pmul = sh_code + prm.K * THREADS;     // PMUL_WORDS words: q * p, q = 0..7
-    pmul_table_fill(sh_pmul, prm.pmul, threadIdx.x);
-    __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31;
     const int K = prm.K;                           // even
     const int c = prm.g.c, W = prm.g.W;
@@ -482,7 +453,7 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
                 fe_mul(lam, t, inv);
                 fe_sqr(t, lam);
                 fe_sub<FpTag, 3>(t, t, u);                 // x3 < 4.2p
-                reduce_loose_tbl(t, sh_pmul);              // < 1.0001p
+                fe_reduce_loose<FpTag>(t);                 // < 1.0001p
                 {
                     FpRaw r;
                     chain_load<THREADS>(r, cs, 0);
@@ -497,7 +468,7 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
                     raw_to_fp(t, r);                       // y1 again
                 }
                 fe_sub<FpTag, 2>(u, u, t);                 // y3 < 3.2p
-                reduce_loose_tbl(u, sh_pmul);
+                fe_reduce_loose<FpTag>(u);
                 chain_store<THREADS>(cs, 1, u);
             }
         }
@@ -549,7 +520,6 @@ __global__ void __maxnreg__(128) k_msm_affine(MsmAffParams prm) { msm_affine_bod
 // no barrier 1.94, out-of-line multiplies 1.92 (profiles/r01/).  248 registers (not 255): 8 warps
 // then leave 2048 registers per SM, enough for one k_sha_blob warp to be co-resident.
 __global__ void __maxnreg__(248) k_msm(MsmParams prm) { msm_body<256, 1, 1, false>(prm); }
-__global__ void __maxnreg__(248) k_msm_g2(MsmParams prm) { msm_body<256, 1, 1, false, 2>(prm); }
 #endif  // RK_TU_MSM
 
 // ---------------------------------------------------------------------------

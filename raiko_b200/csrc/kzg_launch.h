@@ -10,7 +10,6 @@ namespace rk {
 
 #define RK_KERNELS_MSM(X)                                                                      \
     X(k_msm, (MsmParams p), (p))                                                               \
-    X(k_msm_g2, (MsmParams p), (p))                                                            \
     X(k_msm_affine, (MsmAffParams p), (p))
 #define RK_KERNELS_PATH(X)                                                                     \
     X(k_finalize, (const G1Xyzz* partials, int splits, int nblobs, const uint32_t* bad, uint8_t* out_g1, uint8_t* out_vh, uint8_t* status, int stride), \

@@ -4,6 +4,6 @@
 namespace rk {
 RK_KERNELS_MSM(RK_DEFINE_LAUNCH)
 cudaError_t configure_k_msm_affine() {
-    return cudaFuncSetAttribute(k_msm_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (MSM_AFF_MAX_K * MSM_AFF_THREADS + PMUL_WORDS) * 4);
+    return cudaFuncSetAttribute(k_msm_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, MSM_AFF_MAX_K * MSM_AFF_THREADS * 4);
 }
 }  // namespace rk

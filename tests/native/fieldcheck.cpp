@@ -13,7 +13,6 @@ void fc_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y, z; 
 void fc_fr_sqr(const uint32_t* a, uint32_t* r) { Fr x, z; memcpy(x.v, a, 36); fe_sqr(z, x); memcpy(r, z.v, 36); }
 void fc_fp_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y, z; memcpy(x.v, a, 52); memcpy(y.v, b, 52); fe_add(z, x, y); memcpy(r, z.v, 52); }
 void fc_fp_sub6(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y, z; memcpy(x.v, a, 52); memcpy(y.v, b, 52); fe_sub<FpTag, 6>(z, x, y); memcpy(r, z.v, 52); }
-void fc_fp_sub2_3(const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t* r) { Fp x, y, w, z; memcpy(x.v, a, 52); memcpy(y.v, b, 52); memcpy(w.v, c, 52); fe_sub2<FpTag, 3>(z, x, y, w); memcpy(r, z.v, 52); }
 int fc_fp_is_zero_mod(const uint32_t* a) { Fp x; memcpy(x.v, a, 52); return fe_is_zero_mod(x); }
 void fc_fp_pack(const uint32_t* a, uint32_t* w) { Fp x; memcpy(x.v, a, 52); fe_pack<FpTag>(w, x); }
 void fc_fp_unpack(const uint32_t* w, uint32_t* a) { Fp x; fe_unpack<FpTag>(x, w); memcpy(a, x.v, 52); }

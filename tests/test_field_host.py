@@ -142,16 +142,6 @@ def test_safegcd_inversion(L, name, mod, n):
         assert val(out) == 0
 
 
-def test_sub2_single_pass(L):
-    rnd = random.Random(8)
-    for t in range(3000):
-        a = rnd.randrange(2 * P)
-        b, c = (rnd.randrange(2 * P), rnd.randrange(P)) if t else (2 * P - 1, P)
-        out = (ctypes.c_uint32 * 13)()
-        L.fc_fp_sub2_3(limbs(a, 13), limbs(b, 13), limbs(c, 13), out)
-        assert val(out) == a - b - c + 3 * P and all(v < (1 << 30) for v in out[:12])
-
-
 def test_reduce_loose(L):
     rnd = random.Random(77)
     top = P >> 360
