@@ -392,3 +392,43 @@ def test_affine_and_xyzz_kernels_agree(ref, msm_env):
     for i in (0, 1183, n - 1):
         want = ref.commit_prove(blobs[i].cpu().numpy().tobytes())
         assert (out[1].commitments[i], out[1].versioned_hashes[i], out[1].xs[i], out[1].ys[i], out[1].proofs[i]) == want
+
+
+@pytest.mark.parametrize("wb", [8, 15])
+def test_affine_msm_kernel_digit_boundaries(wb, ref, msm_env):
+    """Scalars built to sit on the signed-digit recoding boundaries of k_msm_affine's add-constant
+    recoding (window value exactly 2^(c-1), 2^(c-1) +- 1, all-ones windows that carry into the next
+    one, the largest canonical element, long runs of empty digits), forced through the affine
+    kernel with one warp per blob and checked byte for byte against the C oracle."""
+    import torch
+    import raiko_b200 as rk
+    if wb == 15 and torch.cuda.mem_get_info()[0] < 130e9:
+        pytest.skip("not enough free HBM for the c=15 table")
+    c = wb
+    W = -(-255 // c)
+    half = 1 << (c - 1)
+
+    def blob(fn):
+        return b"".join((fn(i) % R).to_bytes(32, "big") for i in range(4096))
+    blobs = [
+        blob(lambda i: half << (c * (i % W))),                                   # one digit exactly 2^(c-1)
+        blob(lambda i: ((half + 1) << (c * (i % W))) | ((half - 1) << (c * ((i + 3) % (W - 1))))),
+        blob(lambda i: ((1 << c) - 1) * sum(1 << (c * j) for j in range(i % (W - 1) + 1))),   # runs of all-ones windows
+        blob(lambda i: R - 1 - i),                                               # top window at its maximum
+        blob(lambda i: (i & 1) * (1 + (i << 200))),                              # every other element zero
+        blob(lambda i: 1 << (i % 255)),                                          # single bits at every position
+        blob(lambda i: (R - 1) if i == 4095 else 0),                             # one entry in the last lane only
+    ]
+    msm_env(RAIKO_KZG_MSM_AFFINE=2, RAIKO_KZG_AFFINE_MIN_ENTRIES=1, RAIKO_KZG_MAX_SPLITS_LOG2=0)
+    s = rk.KzgSettings(window_bits=wb)
+    try:
+        s.stats_enable(True)
+        s.stats_reset()
+        res = rk.commit_prove_batch(blobs, s)
+        assert s.stats()["msm_affine_launches"] == 2
+        for i, b in enumerate(blobs):
+            want = ref.commit_prove(b)
+            got = (res.commitments[i], res.versioned_hashes[i], res.xs[i], res.ys[i], res.proofs[i])
+            assert got == want and res.status[i] == 0, i
+    finally:
+        s.close()
