@@ -195,10 +195,12 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
 // K = 64: 6.3 M-equivalents per addition instead of 9.6.
 //
 // The chain sums and prefix products do not fit on chip (64 x 156 B per thread), so they live
-// in a per-CTA scratch area in HBM laid out [chain][word][thread]: every access is a fully
-// coalesced 128-byte line per warp, streamed once per round and prefetched one chain ahead
-// (~550 B of traffic per addition, ~2 TB/s at full speed: a third of HBM3e, hidden behind the
-// multiplies).  The kernel is persistent (one CTA per SM) so the scratch is indexed by SM slot.
+// in a per-CTA scratch area in HBM laid out [chain][plane][thread] (ChainScratch below): every
+// access is a run of fully coalesced lines per warp, streamed once per pass.  Measured 707 B of
+// DRAM traffic per addition, 2.3 TB/s at full speed -- a third of HBM3e, traded for a third of the
+// multiplies.  No software prefetch: the kernel is latency-bound, so registers go to resident
+// warps (16 per SM at 128 registers) and operands are re-read where that shortens a live range.
+// The kernel is persistent (one CTA per SM) so the scratch is indexed by SM slot.
 // Scalars are recoded by the add-constant trick (s + H, H = sum half * 2^(cj)) so that a digit
 // can be read at any position without a carry chain; digits of a round are staged in shared
 // memory.  Exceptional additions (equal x: doubling or cancellation) cannot occur between
@@ -214,7 +216,7 @@ struct MsmAffParams {
     G1Xyzz* partials;
     uint32_t* bad;
     uint32_t* scratch;        // gridDim.x * K * AFF_WORDS * block size words
-    int K;                    // chains per lane, 1..64
+    int K;                    // chains per lane, even, 2..64
     int ngroups;              // groups of block-size / 32 warps (one CTA pass each)
     uint32_t H[8];            // recoding constant, little-endian words
 };
