@@ -413,7 +413,7 @@ MsmPlan plan_msm(const DeviceCtx* d, size_t nblobs) {
     // One warp per (blob, split); every warp of a launch does the same amount of work, so a
     // launch runs in whole "waves" of resident warps.  Pick the split AND the formulation that
     // minimise waves x per-warp time.  Per-warp time in units of one XYZZ addition at 8 warps/SM
-    // (measured, profiles/r01/affine_ab_4.txt): k_msm costs its lane's additions plus ~8 for the
+    // (measured, profiles/r01/affine_ab_4_lockstep_groups.txt): k_msm costs its lane's additions plus ~8 for the
     // shuffle tree; k_msm_affine runs 16 warps/SM, each addition 1.36 units, plus ~150 for the
     // chain sums and the tree -- so it wins once a lane owns a few hundred table entries.
     const double adds_per_lane = (double)NPTS * d->geom.W / 32.0;

@@ -2,7 +2,7 @@
 byte-identical to each other and to the C oracle; prints MSM time and additions per second.
 usage: gpu_affine_ab.py [window_bits] [n_blobs] [chains ...]"""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch

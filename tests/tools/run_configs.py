@@ -1,6 +1,6 @@
 """BASELINE.json configs 2..5 on one GPU: latency / throughput table (not the bench line)."""
 import os, sys, time, ctypes, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 import raiko_b200 as rk
