@@ -432,3 +432,53 @@ def test_affine_msm_kernel_digit_boundaries(wb, ref, msm_env):
             assert got == want and res.status[i] == 0, i
     finally:
         s.close()
+
+
+def test_affine_msm_kernel_doubling_and_cancellation(pyoracle, setup_bytes, msm_env):
+    """The additions k_msm_affine's shared-inversion formula cannot do -- a chain sum meeting a
+    table point with the same x (doubling, cancellation) -- cannot happen with the ceremony's
+    setup, whose discrete logs nobody knows.  A crafted setup with KNOWN logs makes them happen:
+    L_i = (i + 2) G, except L_64 = L_0 and L_96 = L_32.  With c = 8, 64 chains and one warp per blob,
+    lane 0 owns points 0, 32, 64, 96, ... and the windows of points 0 / 64 (and 32 / 96) land on the
+    same chains, so equal scalars double a chain sum, opposite low digits cancel it, and a later
+    entry restarts the emptied chain.  Commitments must still be bit-exact (slow path through the
+    complete XYZZ formula, g1_affine_add_slow)."""
+    import struct
+    import raiko_b200 as rk
+    o, real = pyoracle
+    pts, acc = [], o.g1_add(o.G1_GEN, o.G1_GEN)
+    for i in range(4096):
+        pts.append(acc)
+        acc = o.g1_add(acc, o.G1_GEN)
+    pts[64], pts[96] = pts[0], pts[32]
+    image = bytearray(b"RKZGTS02" + struct.pack("<II", 4096, len(real.g2)))
+    for p in pts:
+        image += o.g1_compress(p)
+    image += setup_bytes[16 + 48 * 4096:]                      # the real G2 part (unused by commitments)
+    custom = o.load_settings(bytes(image))
+
+    def blob(vals):
+        b = bytearray(131072)
+        for i, v in vals.items():
+            b[32 * i:32 * i + 32] = (v % R).to_bytes(32, "big")
+        return bytes(b)
+    blobs = [
+        blob({0: 5, 64: 5}),                                   # 5 L_0 + 5 L_0: doubling inside chain 0
+        blob({0: 5, 64: 251}),                                 # 251 = -5 + 256: chain 0 cancels to infinity, chain 1 gets 256 L_0
+        blob({0: 5, 64: 251, 128: 7}),                         # ... and chain 0 restarts with 7 L_128
+        blob({32: 0x0102, 96: 0x0102, 0: 3, 64: 253, 1: 9}),   # two chains double, one cancels, unrelated lane
+        blob({i: (i * 0x9E3779B97F4A7C15 + 1) % R for i in range(4096)}),   # generic scalars on the degenerate setup
+    ]
+    want = [o.blob_to_kzg_commitment(b, custom) for b in blobs]
+    assert want[0] == o.g1_compress(o.g1_mul(o.G1_GEN, 20)) and want[1] == o.g1_compress(o.g1_mul(o.G1_GEN, 512))
+    for affine in (2, 0):                                      # the affine kernel forced, then the XYZZ kernel
+        msm_env(RAIKO_KZG_MSM_AFFINE=affine, RAIKO_KZG_AFFINE_MIN_ENTRIES=1, RAIKO_KZG_MAX_SPLITS_LOG2=0)
+        s = rk.KzgSettings(bytes(image), window_bits=8)
+        try:
+            s.stats_enable(True)
+            s.stats_reset()
+            res = rk.commit_batch(blobs, s)
+            assert (s.stats()["msm_affine_launches"] == 1) == (affine == 2)
+            assert res.commitments == want and res.status == [0] * len(blobs), "affine=%d" % affine
+        finally:
+            s.close()
