@@ -37,6 +37,26 @@ RK_HD void sha256_init(Sha256State& s) {
     s.h[4] = 0x510e527fu; s.h[5] = 0x9b05688cu; s.h[6] = 0x1f83d9abu; s.h[7] = 0x5be0cd19u;
 }
 
+// One round, written so that the dependent chain through e (and a) is three instructions
+// deep -- rotate, 3-input xor, 3-input add -- instead of the six of the textbook statement:
+// h and d are values of e and a from three rounds earlier, so h + K + W and d + h + K + W are
+// formed off the critical path and the new e and a each take ONE 3-input add after Sigma / Ch.
+// A single SHA-256 chain is pure latency (the blob hash is the critical path of a 6-blob request):
+// used by the rounds-only half of the two-warp hash, 6-blob commit+prove 3.49 -> 3.25 ms.
+RK_HD void sha256_round(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t& e, uint32_t& f, uint32_t& g,
+                        uint32_t& h, uint32_t kw) {
+    const uint32_t hkw = h + kw;
+    const uint32_t dhkw = d + hkw;
+    const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+    const uint32_t ch = g ^ (e & (f ^ g));
+    const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+    const uint32_t mj = (a & b) | (c & (a | b));
+    const uint32_t e_new = dhkw + S1 + ch;
+    const uint32_t t1 = hkw + S1 + ch;
+    const uint32_t a_new = t1 + S0 + mj;
+    h = g; g = f; f = e; e = e_new; d = c; c = b; b = a; a = a_new;
+}
+
 // One compression; w[16] = the block as big-endian words (destroyed).
 RK_HD void sha256_compress(Sha256State& s, uint32_t (&w)[16]) {
     uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
@@ -48,6 +68,8 @@ RK_HD void sha256_compress(Sha256State& s, uint32_t (&w)[16]) {
             uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
             w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
         }
+        // textbook statement here: with the message schedule interleaved, the one-warp batch
+        // kernel is faster this way (3.3 ms per 4736 blobs against 4.0 with sha256_round)
         uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
         uint32_t ch = (e & f) ^ (~e & g);
         uint32_t t1 = h + S1 + ch + SHA256_K::at(i) + w[i & 15];
@@ -78,13 +100,7 @@ RK_HD void sha256_rounds(Sha256State& s, const uint32_t* w /* [64], expanded */)
     uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
-        uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
-        uint32_t ch = (e & f) ^ (~e & g);
-        uint32_t t1 = h + S1 + ch + SHA256_K::at(i) + w[i];
-        uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
-        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-        uint32_t t2 = S0 + mj;
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        sha256_round(a, b, c, d, e, f, g, h, SHA256_K::at(i) + w[i]);
     }
     s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
