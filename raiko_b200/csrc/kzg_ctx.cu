@@ -379,7 +379,7 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
     CUDA_TRY(cudaStreamCreateWithFlags(&d->s_out, cudaStreamDefault));
     rk_status st = load_setup(d, settings, len, g2_be);
     if (st != RK_OK) return st;
-    CUDA_TRY(cudaMalloc(&d->roots, sizeof(Fr) * NPTS));
+    CUDA_TRY(cudaMalloc(&d->roots, sizeof(Fr) * 2 * NPTS));    // w R, then w R^2 (k_fr_eval_quot)
     launch_k_roots_brp(NPTS / 128, 128, 0, 0, d->roots);
     CUDA_TRY(cudaGetLastError());
     st = build_table(d);

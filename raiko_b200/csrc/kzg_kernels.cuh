@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(64) k_sha_blob_duo(const uint8_t* blobs, int n
 // ---------------------------------------------------------------------------
 struct FrParams {
     const uint8_t* blobs;       // nblobs * 131072
-    const Fr* roots_brp;        // 4096 Montgomery
+    const Fr* roots_brp;        // 4096 Montgomery (w R), then 4096 doubly scaled (w R^2)
     const uint8_t* blob_hash;   // 32 bytes per blob at out_stride (mode 0)
     const uint8_t* vh;          // 32 bytes per blob at out_stride (mode 0)
     const uint8_t* z_in;        // nblobs * 32, dense (mode 1)
@@ -859,12 +859,12 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
             fe_mul(inv_run, inv_run, d);
         }
         inv_s[i] = inv_i;
-        Fr pc, pm, t;
+        Fr pc, t;
         bool g;
         fr_load_be(pc, g, bp + 32 * i);
         bad |= g;
-        fe_to_mont(pm, pc);
-        fe_mul(t, pm, w);
+        const Fr w2 = prm.roots_brp[NPTS + i];
+        fe_mul(t, pc, w2);                             // p_i w_i in Montgomery form, p_i taken as stored
         fe_mul(t, t, inv_i);
         fe_add(sum, sum, t);                           // < 4096 * 1.1 r, fits 270 bits
     }
@@ -891,9 +891,10 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
             fe_mul(y, total, zp);
         }
         bc_s[1] = y;
+        Fr yc;
+        fe_from_mont(yc, y);
+        bc_s[2] = yc;
         if (prm.out_y) {
-            Fr yc;
-            fe_from_mont(yc, y);
             uint8_t* oy = prm.out_y + (size_t)prm.out_stride * blob;
             uint32_t w[8];
             fe_pack<FrTag>(w, yc);
@@ -903,7 +904,7 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
     }
     __syncthreads();
     if (!prm.want_quotient) return;
-    const Fr y = bc_s[1];
+    const Fr yc = bc_s[2];                              // canonical y: the quotient is formed on canonical values
     uint8_t* qp = prm.q_out + (size_t)blob * BLOB_BYTES;
 
     // ---- phase D: q_i = (y - p_i) * 1/(z - w_i) ----------------------------------------
@@ -912,19 +913,18 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
     for (int k = 0; k < FR_PER_THREAD; k++) {
         const int i = k * FR_THREADS + tid;   // interleaved: coalesced loads, conflict-free smem
         if (i == m) continue;
-        Fr pc, pm, t, q, qc;
+        Fr pc, t, qc;
         bool g;
         fr_load_be(pc, g, bp + 32 * i);
-        fe_to_mont(pm, pc);
-        fe_sub<FrTag, 2>(t, y, pm);                    // y - p_i  (< 4r)
-        Fr inv_i = inv_s[i];
-        fe_mul(q, t, inv_i);
-        fe_from_mont(qc, q);
+        fe_sub<FrTag, 3>(t, yc, pc);                   // y - p_i + 3r on canonical integers (p_i < 2^256 < 3r)
+        Fr inv_i = inv_s[i];                           // Montgomery form: its factor R cancels the product's 1/R
+        fe_mul(qc, t, inv_i);                          // q_i itself, < r + epsilon
+        fe_cond_sub_mod<FrTag>(qc);
         fr_store_be(qp + 32 * i, qc);
         if (m >= 0) {
             // q_m = sum_{i != m} (p_i - y) w_i / (z (z - w_i)) = -(1/z) sum q_i w_i   (App. B.4)
             Fr w = prm.roots_brp[i];
-            fe_mul(t, q, w);
+            fe_mul(t, qc, w);                          // q_i w_i, plain value again
             fe_add(sum_m, sum_m, t);
         }
     }
@@ -937,9 +937,10 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
             fe_zero(total);
             for (int k = 0; k < FR_THREADS; k++) fe_add(total, total, tot_s[k]);
             fe_inv(zinv, z);
-            fe_mul(qm, total, zinv);
-            fe_neg<FrTag, 2>(qm, qm);
-            fe_from_mont(qc, qm);
+            fe_mul(qm, total, zinv);                   // plain total times Montgomery 1/z: plain again, < r + epsilon
+            fe_neg<FrTag, 2>(qc, qm);                  // in (0, 2r]
+            fe_cond_sub_mod<FrTag>(qc);
+            fe_cond_sub_mod<FrTag>(qc);
             fr_store_be(qp + 32 * m, qc);
         }
     }
@@ -1044,6 +1045,11 @@ __global__ void k_roots_brp(Fr* out) {
         fe_sqr(base, base);
     }
     out[i] = acc;
+    // second table: w R^2, so that mul(canonical p, .) is already the Montgomery form of p w
+    Fr r2, acc2;
+    fe_const<FrTag, FR_R2>(r2);
+    fe_mul(acc2, acc, r2);
+    out[NPTS + i] = acc2;
 }
 // w^e(i) in the reference's Montgomery layout (R = 2^256, 4 x u64 LE) for export.
 // order 0: e = i (expanded, n = 4097); 1: e = 4096 - i (reverse); 2: e = brp(i).
