@@ -303,10 +303,11 @@ rk_status build_table(DeviceCtx* d) {
 }
 
 rk_status alloc_slots(DeviceCtx* d) {
-    // chunk: blobs per pipeline stage = four full waves of one-warp-per-blob MSM work
-    // (4 x 148 SMs x 8 warps = 4736 on B200).  A chunk that is not a whole number of waves idles
-    // SMs in its last wave (1024 blobs/chunk measured 13 % slower), and the per-chunk fixed costs
-    // (hash latency, finalize, launch gaps) amortise over more blobs.
+    // chunk: blobs per pipeline stage = a whole number of waves of one-warp-per-blob MSM work:
+    // 4736 on B200 = 2 waves of k_msm_affine (148 SMs x 16 warps) = 4 waves of k_msm (x 8 warps).
+    // A chunk that is not a whole number of waves idles SMs in its last wave (1024 blobs/chunk
+    // measured 13 % slower), and the per-chunk fixed costs (hash latency, finalize, launch gaps)
+    // amortise over more blobs.
     // 2 slots x (blobs + quotients: 128 KiB each, inversion scratch: 144 KiB) per blob = 3.8 GB.
     d->chunk = 4 * d->sm_count * d->warps_per_sm;
     if (const char* e = getenv("RAIKO_KZG_CHUNK")) {
