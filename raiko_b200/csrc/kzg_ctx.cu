@@ -108,6 +108,7 @@ struct DeviceCtx {
     // RAIKO_KZG_SHA_SERIAL=0) its latency-bound warps sit in the MSM's issue slots and cost the
     // MSM 3-6 %, more than the 3.3 ms per chunk the hash takes alone.
     bool sha_serial = true;
+    bool sha_duo = true;                   // two-warp hash (schedule / rounds split); RAIKO_KZG_SHA_DUO=0: one warp
     // MSM formulation (RAIKO_KZG_MSM_AFFINE): 1 = batched affine additions (k_msm_affine) where the
     // planner estimates them faster, i.e. launches whose lanes own a few hundred table entries;
     // 0 = XYZZ only (k_msm); 2 = affine wherever eligible (tests).
@@ -353,6 +354,7 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
     CUDA_TRY(cudaGetDeviceProperties(&prop, d->dev));
     d->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("RAIKO_KZG_SHA_SERIAL")) d->sha_serial = atoi(e) != 0;
+    if (const char* e = getenv("RAIKO_KZG_SHA_DUO")) d->sha_duo = atoi(e) != 0;
     d->warps_per_sm = 8;                   // k_msm: 256-thread CTAs at 248 registers
     if (prop.major < 10)
         return fail(RK_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", d->dev, prop.major, prop.minor);
@@ -529,9 +531,8 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             cudaStream_t hs = serial ? d->s_main : d->s_sha;
             if (!serial) CUDA_TRY(cudaStreamWaitEvent(d->s_sha, s.ev_in, 0));
             timer_begin(d, hs, T_SHA);
-            // <= 8 blobs (a Cancun block has <= 6): the MSM leaves SMs free, use the two-warp hash.
-            // Larger batches keep the one-warp kernel, whose 2048 registers fit beside an MSM CTA.
-            if (cnt <= 8) launch_k_sha_blob_duo(cnt, 64, 0, hs, d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
+            // Two-warp hash (lane = blob; schedule and rounds on separate warps) for every batch size.
+            if (d->sha_duo) launch_k_sha_blob_duo((cnt + 31) / 32, 64, 0, hs, d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
             else launch_k_sha_blob((cnt + 31) / 32, 32, 0, hs, d_blobs, cnt, o + OFF_HASH, OUT_STRIDE);
             timer_end(d, hs);
             CUDA_TRY(cudaEventRecord(s.ev_sha, hs));

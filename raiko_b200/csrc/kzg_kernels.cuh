@@ -650,20 +650,27 @@ __global__ void __launch_bounds__(32) k_sha_blob(const uint8_t* blobs, int nblob
 // the message schedule of block i+1 (on another sub-partition) while warp 0 runs the 64 rounds of
 // block i, handing W[64] over through shared memory: ~1.8x faster per blob.
 __global__ void __launch_bounds__(64) k_sha_blob_duo(const uint8_t* blobs, int nblobs, uint8_t* out_hash, int stride) {
-    __shared__ uint32_t wbuf[2][64];
-    const int blob = blockIdx.x;
+    // Two warps per 32 blobs, lane = blob: warp 1 expands the message schedule of block b while
+    // warp 0 runs the 64 rounds of block b-1, the 64 expanded words handed over through shared
+    // memory ([word][lane]: conflict-free).  A SHA-256 chain is pure latency; splitting it this way
+    // takes the schedule off the rounds' dependent chain (2.2 ms per 128 KiB blob against 3.3 ms
+    // for the one-warp kernel, for 6 blobs and for 4736 alike).
+    __shared__ uint32_t wbuf[2][64][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blob_raw = blockIdx.x * 32 + lane;
+    const bool live = blob_raw < nblobs;
+    const int blob = live ? blob_raw : nblobs - 1;       // idle lanes shadow the last blob: uniform barriers
     const uint4* p = reinterpret_cast<const uint4*>(blobs + (size_t)blob * BLOB_BYTES);
     constexpr int NB = BLOB_BYTES / 64 + 1;              // data blocks + the padding block
     Sha256State st;
     sha256_init(st);
     uint4 nx[4];
-    if (warp == 1 && lane == 0) {
+    if (warp == 1) {
 #pragma unroll
         for (int q = 0; q < 4; q++) nx[q] = ldg_nc(p + q);
     }
     for (int b = 0; b <= NB; b++) {
-        if (warp == 1 && lane == 0 && b < NB) {          // producer: schedule of block b
+        if (warp == 1 && b < NB) {                       // producer: schedule of block b
             uint32_t blk[16];
             if (b < NB - 1) {
 #pragma unroll
@@ -682,12 +689,20 @@ __global__ void __launch_bounds__(64) k_sha_blob_duo(const uint8_t* blobs, int n
                 blk[0] = 0x80000000u;
                 blk[15] = (uint32_t)BLOB_BYTES * 8u;
             }
-            sha256_schedule(wbuf[b & 1], blk);
+            uint32_t w[64];
+            sha256_schedule(w, blk);
+#pragma unroll
+            for (int i = 0; i < 64; i++) wbuf[b & 1][i][lane] = w[i];
         }
-        if (warp == 0 && lane == 0 && b > 0) sha256_rounds(st, wbuf[(b - 1) & 1]);   // consumer: rounds of block b-1
+        if (warp == 0 && b > 0) {                        // consumer: rounds of block b-1
+            uint32_t w[64];
+#pragma unroll
+            for (int i = 0; i < 64; i++) w[i] = wbuf[(b - 1) & 1][i][lane];
+            sha256_rounds(st, w);
+        }
         __syncthreads();
     }
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && live) {
         uint8_t* o = out_hash + (size_t)stride * blob;
         for (int i = 0; i < 8; i++) store_be32(o + 4 * i, st.h[i]);
     }
