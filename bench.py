@@ -4,16 +4,21 @@
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-A "step" is one pass of the hot path over one batch of synthetic blobs per GPU:
-commitment -> versioned hash -> raiko challenge -> evaluation -> KZG proof
-(rk_commit_prove_batch).  Default batch: the 65,536-blob batch BASELINE.json quotes the
-metric on (configs[3]); blobs are independent, so ranks shard with no collective and
-scaling is weak (every rank runs its own 65,536-blob batch).
+A "step" is one pass of the hot path over ONE batch of synthetic blobs: commitment -> versioned
+hash -> raiko challenge -> evaluation -> KZG proof (rk_commit_prove_batch).  The batch is the
+65,536-blob batch BASELINE.json quotes the metric on (configs[3]).  Blobs are independent, so at
+N > 1 the batch is sharded contiguously over the ranks with no collective and the line says
+"scaling": "strong" (rank r owns blobs shard_range(65536, r, N); `value` = 65,536 x steps / the
+max-over-ranks device time).  `--scaling weak` gives every rank its own 65,536 blobs instead.
 
-Prints ONE JSON line (rank 0).  `value` = blobs/s with inputs resident in HBM, `e2e` = the
-same through the C ABI with HOST buffers (pinned; H2D/D2H inside the timed region),
-`roofline` = the MSM kernel against the measured integer-multiply peak, `cpu_baseline` =
-the C restatement of the reference path on this box's host cores.
+Prints ONE JSON line (rank 0).  `value` = blobs/s with inputs resident in HBM, `e2e` = the same
+through the C ABI with HOST buffers (pinned; H2D/D2H inside the timed region), `roofline` = the MSM
+kernel against the measured integer-multiply peak (executed instructions from the committed ncu
+opcode histogram, profiles/roofline_inputs.json), `cpu_baseline` = the C restatement of the
+reference path on this box's host cores.  At N = 1 the line also carries `configs`: BASELINE.json
+configs[1], [2] and [4] (6-blob latency, 4096-blob commitment throughput, 4096-blob batch verify).
+At N > 1 it carries `single_process`: ONE process, ONE context over all N GPUs, ONE
+rk_commit_prove_batch call on the whole 65,536-blob host buffer (the library's own sharding).
 """
 import argparse
 import ctypes
@@ -36,13 +41,15 @@ UNIT = "blobs/s"
 # SURVEY.md §8(d) / BASELINE.md §3 work model (shared with the judge):
 MODEL_IMAD_PER_MSM = 540.7e6       # 90 112 adds x 10 Fp-mul x 600 IMAD (c = 13 bucket Pippenger)
 MODEL_IMAD_PER_BLOB = 1.09e9       # commit + proof: 2 MSM + Fr side
-# what this implementation actually issues on the integer-multiply pipe per table addition:
-# madd-2008-s = 8 M + 2 S on 13 x 30-bit limbs = 8*(2*169+13) + 2*(91+169+13) IMAD.WIDE/IMAD
-EXEC_IMAD_PER_ADD = 8 * 351 + 2 * 273
-# k_msm_affine (batched affine additions): 5 M + 1 S per addition, plus per 64 additions one
-# division-step inversion (27 iterations x 132 multiplies) and per 2176 additions 63 XYZZ
-# chain-sum additions
-EXEC_IMAD_PER_ADD_AFFINE = 5 * 351 + 273 + (27 * 132) // 64 + (63 * EXEC_IMAD_PER_ADD) // 2176
+SEED = 20241018                    # the synthetic family of golden vectors C5 / C6
+
+
+def roofline_inputs():
+    """Executed work per point addition of each MSM kernel, MEASURED: the dynamic SASS opcode
+    histogram of an `ncu --set full --import-source on` capture (tools/make_roofline_inputs.py ->
+    profiles/roofline_inputs.json, histograms beside it).  Nothing here is a typed-in constant."""
+    with open(os.path.join(ROOT, "profiles", "roofline_inputs.json")) as f:
+        return json.load(f)
 
 
 def parse_args():
@@ -52,7 +59,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("RAIKO_BENCH_BATCH", "65536")),
-                    help="blobs per GPU per step")
+                    help="blobs per step: the whole job's batch (strong scaling) or per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = ONE batch sharded over the ranks (default); weak = one batch per rank")
+    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the configs[1]/[2]/[4] legs")
+    ap.add_argument("--no-single-process", action="store_true", help="N > 1: skip the one-process multi-device leg")
     ap.add_argument("--window-bits", type=int, default=int(os.environ.get("RAIKO_KZG_WINDOW_BITS", "0")))
     ap.add_argument("--cpu-sample", type=int, default=48, help="blobs timed for cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
@@ -143,13 +154,11 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # CPU reference arm: the C restatement of the reference path (oracle/kzg_ref.c)
 # --------------------------------------------------------------------------------------
-def synth_blobs_host(n: int, seed: int):
-    """Uniform canonical field elements (first byte < 0x73 => value < r), numpy, deterministic."""
-    import numpy as np
-    rng = np.random.default_rng(seed)
-    a = rng.integers(0, 256, size=(n, 4096, 32), dtype=np.uint8)
-    a[:, :, 0] %= 0x73
-    return a
+def synth_blobs_host(n: int, seed: int = SEED, first: int = 0):
+    """The SURVEY.md 8(d) synthetic blobs first .. first+n-1 on the host (hashlib): byte-identical to
+    what rk_synth_blobs writes on the device."""
+    from kzg_testlib import synthetic_blob
+    return [synthetic_blob(first + b, seed) for b in range(n)]
 
 
 def cpu_model() -> str:
@@ -183,8 +192,7 @@ def run_reference(args):
     kzg_ref.build()
     cores = os.cpu_count() or 1
     per_step = max(4 * cores, 64)      # ~1 s of work per host thread per step: thread start-up does not dominate
-    arr = synth_blobs_host(per_step, seed=20241018)
-    blobs = [arr[i].tobytes() for i in range(per_step)]
+    blobs = synth_blobs_host(per_step)
     for _ in range(args.warmup):
         cpu_commit_prove(blobs[:cores], cores)
     t = 0.0
@@ -195,9 +203,10 @@ def run_reference(args):
     sample = "%d synthetic blobs per step on %d host threads (oracle/kzg_ref.c: C restatement of the reference's single-threaded CPU path, one blob per thread)" % (per_step, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64 limbs (Fp 381-bit / Fr 255-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": "commit+versioned_hash+challenge+eval+proof per blob (bounded sample of the 65,536-blob batch)",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "u64 limbs (Fp 381-bit / Fr 255-bit Montgomery)", "data": "synthetic (SURVEY.md 8(d) SHA-256 family, seed %d)" % SEED,
+        "config": {"workload": "BASELINE.json configs[3]: commit+versioned_hash+challenge+eval+proof per blob; each step a bounded sample "
+                               "(the first %d blobs) of the 65,536-blob batch" % per_step,
                    "blobs_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,14 +219,74 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def _ptr(t):
+    return t.data_ptr()
+
+
+def alloc_host(shape, torch):
+    """Pinned when the box lets us lock that much memory, else pageable (said in the line)."""
+    try:
+        return torch.empty(shape, dtype=torch.uint8, pin_memory=True), "pinned"
+    except RuntimeError:
+        return torch.empty(shape, dtype=torch.uint8), "pageable"
+
+
+WIDTHS = (("c", 48), ("vh", 32), ("x", 32), ("y", 32), ("p", 48), ("st", 1))
+
+
+def msm_roofline(stats, msm_kernel_ms, peak, inputs, world_value_per_gpu):
+    """The MSM kernel against the measured integer-multiply peak.
+
+    frac        executed multiply instructions (IMAD.WIDE / IMAD, thread level, from the committed
+                ncu opcode histogram) per second / measured peak.  This is a pipe-utilisation number.
+    slot_frac   the same with IMAD.WIDE Rd,Ra,Rb,Rc64 counted twice (it issues at half rate on B200).
+    model_frac  SURVEY.md 8(d) work model (540.7 M IMAD per MSM) per second / peak: a SPEED-UP over the
+                model algorithm, not a utilisation -- the kernel executes far fewer multiplies.
+    pipe_busy   sm__pipe_fmaheavy_cycles_active of the same ncu capture."""
+    adds = stats["msm_point_adds"]
+    aff_adds = stats.get("msm_affine_point_adds", 0)
+    msm_s = stats["msm_ms"] / 1e3
+    launches = max(1, stats["msm_launches"])
+    kern = "k_msm_affine" if 2 * aff_adds > adds else "k_msm"
+    ia, ix = inputs["k_msm_affine"], inputs["k_msm"]
+    mul_inst = ia["multiply_thread_inst_per_unit"] * aff_adds + ix["multiply_thread_inst_per_unit"] * (adds - aff_adds)
+    mul_slots = ia["mul_pipe_thread_slots_per_unit"] * aff_adds + ix["mul_pipe_thread_slots_per_unit"] * (adds - aff_adds)
+    all_inst = ia["thread_inst_per_unit"] * aff_adds + ix["thread_inst_per_unit"] * (adds - aff_adds)
+    msms = stats["_msms"]
+    windows = adds / max(1, msms) / 4096.0
+    k = inputs[kern]
+    return {
+        "bound": "imad", "kernel": kern, "unit": "T multiply instr/s (thread level)",
+        "achieved": mul_inst / msm_s / 1e12, "peak": peak / 1e12, "frac": mul_inst / msm_s / peak,
+        "slot_frac": mul_slots / msm_s / peak, "model_frac": MODEL_IMAD_PER_MSM * msms / msm_s / peak,
+        "pipe_busy": k["pipe_busy_fmaheavy"], "issue_active": k["issue_active"],
+        "traffic": k["dram_bytes_per_launch"], "traffic_units_per_launch": k["units_per_launch"],
+        "dram_bytes_per_point_add": k["dram_bytes_per_unit"], "algorithmic_bytes_per_point_add": 96 + BLOB / (4096.0 * windows),
+        "peak_source": "measured in this run: dependency-free mad.wide.u32 on all SMs (rk_measure_imad_peak); MEASURED_PEAKS.json has no integer peak",
+        "work_source": "profiles/roofline_inputs.json <- %s (ncu --set full --import-source on; per-instruction executed counts)" % k["source_report"],
+        "thread_inst_per_point_add": k["thread_inst_per_unit"], "multiply_inst_per_point_add": k["multiply_thread_inst_per_unit"],
+        "all_inst_per_s_T": all_inst / msm_s / 1e12,
+        "work_model": "SURVEY.md 8(d): 540.7e6 IMAD per 4096-term MSM (c=13 bucket Pippenger, 600 IMAD per Fp mul) -> model_frac",
+        "msm_share_of_step": 1e3 * msm_s / msm_kernel_ms if msm_kernel_ms else None,
+        "avg_launch_ms": 1e3 * msm_s / launches, "msm_per_launch": msms / launches,
+        "windows_per_scalar": windows, "point_adds_per_s": adds / msm_s,
+        "affine_share_of_adds": aff_adds / max(1, adds),
+        "whole_path_model_frac": world_value_per_gpu * MODEL_IMAD_PER_BLOB / peak,
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # host-side barrier for the phases in which a rank's GPU is used by ANOTHER process (the
+        # single-process leg): an NCCL barrier would leave a kernel spinning on that GPU
+        cpu_group = dist.new_group(backend="gloo")
     dev = torch.device("cuda", local)
     import raiko_b200 as rk
     from raiko_b200 import _native
@@ -226,21 +295,17 @@ def run_ours(args):
     t0 = time.time()
     s = rk.KzgSettings(devices=[local], window_bits=args.window_bits)
     setup_s = time.time() - t0
-    B = args.batch
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(20241018 + rank)
+    strong = args.scaling == "strong"
+    total = args.batch if strong else args.batch * world           # blobs of the whole job per step
+    lo, hi = shard_range(total, rank, world) if strong else (rank * args.batch, (rank + 1) * args.batch)
+    B = hi - lo                                                     # this rank's shard
     blobs = torch.empty((B, 4096, 32), dtype=torch.uint8, device=dev)
-    step = 4096
-    for i in range(0, B, step):       # chunked so the generator's temporaries stay small
-        j = min(B, i + step)
-        blobs[i:j] = torch.randint(0, 256, (j - i, 4096, 32), dtype=torch.uint8, device=dev, generator=gen)
-    blobs[:, :, 0] %= 0x73            # canonical: every field element < r, full-width otherwise
-    widths = (("c", 48), ("vh", 32), ("x", 32), ("y", 32), ("p", 48), ("st", 1))
-    outs = {k: torch.zeros((B, w), dtype=torch.uint8, device=dev) for k, w in widths}
+    s.synth_blobs(blobs, first_blob=lo, seed=SEED)                  # SURVEY.md 8(d) family, generated on the device
+    outs = {k: torch.zeros((B, w), dtype=torch.uint8, device=dev) for k, w in WIDTHS}
 
     def step_device():
-        st = lib.rk_commit_prove_batch(s._ctx, blobs.data_ptr(), B, outs["c"].data_ptr(), outs["vh"].data_ptr(),
-                                       outs["x"].data_ptr(), outs["y"].data_ptr(), outs["p"].data_ptr(), outs["st"].data_ptr())
+        st = lib.rk_commit_prove_batch(s._ctx, _ptr(blobs), B, _ptr(outs["c"]), _ptr(outs["vh"]),
+                                       _ptr(outs["x"]), _ptr(outs["y"]), _ptr(outs["p"]), _ptr(outs["st"]))
         if st != 0:
             raise RuntimeError(_native.last_error())
 
@@ -267,17 +332,30 @@ def run_ours(args):
     dev_s = e0.elapsed_time(e1) / 1e3
     t_max = max_over_ranks(dev_s, world, dev)
     stats = s.stats()
+    stats["_msms"] = 2 * B * args.steps                   # commit + proof MSM per blob
     s.stats_enable(False)
-    value = world * B * args.steps / t_max
+    value = total * args.steps / t_max
 
-    # ---- parity spot-check of the timed outputs against the oracle (rank 0) -------------
+    # ---- parity of the timed outputs (rank 0): golden vectors C5 / C6 + the oracle --------------
     parity_n = 0
     if rank == 0:
         import kzg_ref
-        from kzg_testlib import SETUP
+        from kzg_testlib import SETUP, load_golden, synthetic_blob
         ref = kzg_ref.RefSettings(open(SETUP, "rb").read())
-        for i in (0, B // 3, B - 1):
-            want = ref.commit_prove(blobs[i].cpu().numpy().tobytes())
+        if lo == 0 and B >= 2:
+            # blobs 0 and 1 of this seed ARE SURVEY.md App. C rows C5 / C6 (tests/golden/kzg_golden.json)
+            gold = {c["name"]: c for c in load_golden()["cases"]}
+            for i, name in ((0, "C5_syn0"), (1, "C6_syn1")):
+                g = gold[name]
+                pr = [q for q in g["proofs"] if q["label"] == "raiko"][0]
+                assert outs["c"][i].cpu().numpy().tobytes().hex() == g["commitment"], "bench blob %d: commitment differs from golden %s" % (i, name)
+                assert outs["x"][i].cpu().numpy().tobytes().hex() == pr["z"] and outs["y"][i].cpu().numpy().tobytes().hex() == pr["y"]
+                assert outs["p"][i].cpu().numpy().tobytes().hex() == pr["proof"], "bench blob %d: proof differs from golden %s" % (i, name)
+                parity_n += 1
+        for i in sorted({0, B // 3, B - 1}):
+            host_blob = blobs[i].cpu().numpy().tobytes()
+            assert host_blob == synthetic_blob(lo + i, SEED), "device-generated blob %d differs from the host generator" % (lo + i)
+            want = ref.commit_prove(host_blob)
             got = tuple(outs[k][i].cpu().numpy().tobytes() for k in ("c", "vh", "x", "y", "p"))
             assert got == want and int(outs["st"][i]) == 0, "bench output differs from the oracle at blob %d" % i
             parity_n += 1
@@ -285,20 +363,15 @@ def run_ours(args):
 
     # ---- end-to-end leg: host buffers through the C ABI ----------------------------------
     e2e = None
+    keep = {k: outs[k].cpu() for k, _ in WIDTHS}                     # for the cross-checks below
     if not args.no_e2e:
-        Be = B
-        host_kind = "pinned"
-        try:
-            h_in = torch.empty((Be, 4096, 32), dtype=torch.uint8, pin_memory=True)
-        except RuntimeError:                      # not enough lockable memory on this box
-            host_kind = "pageable"
-            h_in = torch.empty((Be, 4096, 32), dtype=torch.uint8)
-        h_in.copy_(blobs[:Be])
-        h_out = {k: torch.zeros((Be, w), dtype=torch.uint8, pin_memory=(host_kind == "pinned")) for k, w in widths}
+        h_in, host_kind = alloc_host((B, 4096, 32), torch)
+        h_in.copy_(blobs)
+        h_out = {k: torch.zeros((B, w), dtype=torch.uint8, pin_memory=(host_kind == "pinned")) for k, w in WIDTHS}
 
         def step_host():
-            st = lib.rk_commit_prove_batch(s._ctx, h_in.data_ptr(), Be, h_out["c"].data_ptr(), h_out["vh"].data_ptr(),
-                                           h_out["x"].data_ptr(), h_out["y"].data_ptr(), h_out["p"].data_ptr(), h_out["st"].data_ptr())
+            st = lib.rk_commit_prove_batch(s._ctx, _ptr(h_in), B, _ptr(h_out["c"]), _ptr(h_out["vh"]),
+                                           _ptr(h_out["x"]), _ptr(h_out["y"]), _ptr(h_out["p"]), _ptr(h_out["st"]))
             if st != 0:
                 raise RuntimeError(_native.last_error())
         e2e_steps = max(1, min(args.steps, 3))      # bounded so a large --steps does not double the run time
@@ -308,65 +381,26 @@ def run_ours(args):
         barrier(world)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            step_host()
-        torch.cuda.synchronize()
+            step_host()                             # returns when every output byte is in the host arrays
         te = time.perf_counter() - t0
         barrier(world)
         te = max_over_ranks(te, world, dev)
-        assert bytes(h_out["c"][Be - 1].numpy().tobytes()) == outs["c"][Be - 1].cpu().numpy().tobytes()
-        e2e = {"value": world * Be * e2e_steps / te, "unit": UNIT, "h2d_bytes_per_step": Be * BLOB,
-               "d2h_bytes_per_step": Be * 225, "host_memory": host_kind, "ms_per_step": 1e3 * te / e2e_steps,
-               "steps": e2e_steps, "api": "rk_commit_prove_batch(host pointers): chunked H2D + kernels + D2H inside the timed region"}
-        del h_in
+        for k, _ in WIDTHS:
+            assert torch.equal(h_out[k], keep[k]), "host-buffer outputs differ from the device-resident leg (%s)" % k
+        e2e = {"value": total * e2e_steps / te, "unit": UNIT, "h2d_bytes_per_step": total * BLOB,
+               "d2h_bytes_per_step": total * 225, "host_memory": host_kind, "ms_per_step": 1e3 * te / e2e_steps,
+               "steps": e2e_steps, "timing": "host wall clock around the blocking C-ABI calls, max over ranks",
+               "api": "rk_commit_prove_batch(host pointers): chunked H2D + kernels + D2H inside the timed region"}
+        del h_in, h_out
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+    # ---- N = 1: the other BASELINE.json configs, driver-visible ----------------------------------
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = run_configs(torch, rk, lib, _native, s, blobs, keep)
 
-    # ---- roofline of the dominant kernel (k_msm) ------------------------------------------
     peak, clkattr = ctypes.c_double(), ctypes.c_double()
-    lib.rk_measure_imad_peak(local, ctypes.byref(peak), ctypes.byref(clkattr))
-    msm_launches = max(1, stats["msm_launches"])
-    msm_s = stats["msm_ms"] / 1e3
-    msms_done = 2 * B * args.steps                       # commit + proof MSM per blob
-    avg_launch_s = msm_s / msm_launches
-    msm_per_launch = msms_done / msm_launches
-    achieved = MODEL_IMAD_PER_MSM * msm_per_launch / avg_launch_s          # algorithmic IMAD/s (work model)
-    aff_adds = stats.get("msm_affine_point_adds", 0)
-    executed = (EXEC_IMAD_PER_ADD * (stats["msm_point_adds"] - aff_adds) + EXEC_IMAD_PER_ADD_AFFINE * aff_adds) / msm_s   # issued on the multiply pipe
-    msm_kernel = "k_msm_affine" if 2 * aff_adds > stats["msm_point_adds"] else "k_msm"
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "msm_dram_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except Exception:  # noqa: BLE001
-            traffic = None
-    geom_w = stats["msm_point_adds"] / max(1, msms_done) / 4096
-    roofline = {
-        "bound": "imad", "kernel": msm_kernel, "achieved": achieved / 1e12, "peak": peak.value / 1e12, "unit": "TIMAD/s",
-        "frac": achieved / peak.value, "traffic": traffic,
-        "peak_source": "measured in this run: dependency-free mad.wide.u32 on all SMs (rk_measure_imad_peak); MEASURED_PEAKS.json has no integer peak",
-        "work_model": "SURVEY.md 8(d): 540.7e6 IMAD per 4096-term MSM (c=13 bucket Pippenger, 600 IMAD per Fp mul)",
-        "msm_share_of_step": msm_s / (dev_s if dev_s > 0 else 1),
-        "avg_launch_ms": 1e3 * avg_launch_s, "msm_per_launch": msm_per_launch,
-        "executed_timad_per_s": executed / 1e12, "frac_executed": executed / peak.value,
-        "windows_per_scalar": geom_w,
-        "table_read_gbs": stats["msm_point_adds"] * 96 / msm_s / 1e9,
-        "point_adds_per_s": stats["msm_point_adds"] / msm_s, "affine_share_of_adds": aff_adds / max(1, stats["msm_point_adds"]),
-        "whole_path_frac": value / world * MODEL_IMAD_PER_BLOB / peak.value,
-    }
-
-    hbm_peak = None
-    try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    except Exception:  # noqa: BLE001
-        hbm_peak = 6650.0     # B200_PROFILING.md fallback
-    alg_bytes_per_msm = 4096 * geom_w * 96 + BLOB          # table entries + the scalars
-    roofline_hbm = {"bound": "hbm", "kernel": msm_kernel, "achieved": alg_bytes_per_msm * msm_per_launch / avg_launch_s / 1e9,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes_per_msm * msm_per_launch / avg_launch_s / 1e9 / hbm_peak,
-                    "traffic": traffic, "note": "algorithmic bytes = one 96-byte table entry per addition + the scalars; k_msm_affine deliberately streams ~600 B more per addition (chain sums, prefix products) through HBM to save multiplies; the kernel is multiply/issue bound, not HBM bound"}
+    if rank == 0:
+        lib.rk_measure_imad_peak(local, ctypes.byref(peak), ctypes.byref(clkattr))
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores -------------
     cpu = None
@@ -376,20 +410,59 @@ def run_ours(args):
         sample = [blobs[i].cpu().numpy().tobytes() for i in range(ncpu)]
         dt, res = cpu_commit_prove(sample, cores)
         for i in (0, ncpu - 1):
-            got = tuple(outs[k][i].cpu().numpy().tobytes() for k in ("c", "vh", "x", "y", "p"))
+            got = tuple(keep[k][i].numpy().tobytes() for k in ("c", "vh", "x", "y", "p"))
             assert got == res[i]
         dt1, _ = cpu_commit_prove(sample[:4], 1)
         cpu = {"value": ncpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d blobs of the timed batch, one blob per thread on %d threads (oracle/kzg_ref.c)" % (ncpu, cores),
                "single_thread_value": 4 / dt1, "cpu_model": cpu_model()}
 
+    # ---- N > 1: ONE process, ONE context over all GPUs, ONE call on the whole host batch ---------
+    single = None
+    table_bytes, window_bits = s.table_bytes, s.window_bits
+    if world > 1 and strong and not args.no_single_process:
+        s.close()
+        del blobs, outs
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)               # every rank has released its table
+        if rank == 0:
+            single = run_single_process(torch, rk, lib, _native, args, world, total, keep, lo, hi)
+        dist.barrier(group=cpu_group)               # host-side wait: no kernel parked on the other GPUs
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    inputs = roofline_inputs()
+    roofline = msm_roofline(stats, 1e3 * dev_s, peak.value, inputs, value / world)
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:  # noqa: BLE001
+        hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback"
+    msm_s = stats["msm_ms"] / 1e3
+    adds = stats["msm_point_adds"]
+    alg_bytes = adds * 96 + stats["_msms"] * BLOB                      # one table entry per addition + the scalars
+    roofline_hbm = {"bound": "hbm", "kernel": roofline["kernel"], "achieved": alg_bytes / msm_s / 1e9, "peak": hbm_peak, "peak_source": hbm_src,
+                    "unit": "GB/s", "frac": alg_bytes / msm_s / 1e9 / hbm_peak,
+                    "traffic_gbs": roofline["dram_bytes_per_point_add"] * adds / msm_s / 1e9,
+                    "traffic_frac": roofline["dram_bytes_per_point_add"] * adds / msm_s / 1e9 / hbm_peak,
+                    "note": "algorithmic bytes = one 96-byte table entry per addition + the scalars; k_msm_affine deliberately streams its "
+                            "chain sums and prefix products through HBM (traffic_gbs, from the ncu capture) to save multiplies; the kernel "
+                            "is multiply/issue bound, not HBM bound"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 limbs (13 x 30-bit Fp, 9 x 30-bit Fr Montgomery; IMAD.WIDE)", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[3]: 65,536-blob batch, commit+versioned_hash+challenge+eval+proof per blob"
-                   if B == 65536 else "commit+versioned_hash+challenge+eval+proof per blob, %d blobs per GPU per step" % B,
-                   "blobs_per_gpu_per_step": B, "window_bits": s.window_bits, "table_gb_per_gpu": s.table_bytes / 1e9,
+        "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "u32 limbs (13 x 30-bit Fp, 9 x 30-bit Fr Montgomery; IMAD.WIDE)",
+        "data": "synthetic (SURVEY.md 8(d) SHA-256 family, seed %d, generated on the device by rk_synth_blobs; blobs 0/1 = golden C5/C6)" % SEED,
+        "config": {"workload": ("BASELINE.json configs[3]: ONE 65,536-blob batch, commit+versioned_hash+challenge+eval+proof per blob"
+                                if total == 65536 else "commit+versioned_hash+challenge+eval+proof per blob, %d blobs per step" % total)
+                               + (", sharded contiguously over %d GPUs (host-side gather, no collective)" % world if world > 1 else ""),
+                   "blobs_per_step": total, "blobs_per_gpu_per_step": B, "window_bits": window_bits, "table_gb_per_gpu": table_bytes / 1e9,
                    "inputs": "resident in HBM (%.1f GB per GPU, > 126 MB L2: no flush needed)" % (B * BLOB / 1e9),
                    "parallelism": "dp%d (independent blobs, no collective)" % world, "setup_seconds": setup_s},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(stats["total_launches"]),
@@ -397,10 +470,116 @@ def run_ours(args):
         "kernel_ms": {k: stats[k] for k in ("msm_ms", "fr_ms", "sha_ms", "finalize_ms")},
         "host_wall_ms_per_step": 1e3 * (w1 - w0) / args.steps, "parity_checked_blobs": parity_n,
     }
+    if configs is not None:
+        line["configs"] = configs
+    if single is not None:
+        line["single_process"] = single
     emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_single_process(torch, rk, lib, _native, args, world, total, keep, lo, hi):
+    """The API shape BASELINE.json's north_star describes: one host process, one context over all
+    N GPUs, one rk_commit_prove_batch call on the whole batch in host memory; the library shards
+    contiguously (one host thread per device) and gathers on the host."""
+    t0 = time.time()
+    sp = rk.KzgSettings(devices=list(range(world)), window_bits=args.window_bits)
+    setup_s = time.time() - t0
+    h_in, host_kind = alloc_host((total, 4096, 32), torch)
+    sp.synth_blobs(h_in, first_blob=0, seed=SEED)
+    h_out = {k: torch.zeros((total, w), dtype=torch.uint8, pin_memory=(host_kind == "pinned")) for k, w in WIDTHS}
+
+    def step():
+        st = lib.rk_commit_prove_batch(sp._ctx, _ptr(h_in), total, _ptr(h_out["c"]), _ptr(h_out["vh"]),
+                                       _ptr(h_out["x"]), _ptr(h_out["y"]), _ptr(h_out["p"]), _ptr(h_out["st"]))
+        if st != 0:
+            raise RuntimeError(_native.last_error())
+    step()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    # rank 0's shard was computed by this rank's own context before: the gathered outputs must agree
+    for k, _ in WIDTHS:
+        assert torch.equal(h_out[k][lo:hi], keep[k]), "single-process multi-device outputs differ from the per-rank leg (%s)" % k
+    assert int(h_out["st"].sum()) == 0
+    res = {"value": total * steps / dt, "unit": UNIT, "devices": world, "steps": steps, "ms_per_step": 1e3 * dt / steps,
+           "host_memory": host_kind, "window_bits": sp.window_bits, "setup_seconds": setup_s,
+           "h2d_bytes_per_step": total * BLOB, "d2h_bytes_per_step": total * 225,
+           "api": "rk_kzg_ctx_create(devices=[0..%d]) + ONE rk_commit_prove_batch(host pointers, %d blobs)" % (world - 1, total),
+           "checked": "blobs [%d, %d) equal the per-rank leg byte for byte; all statuses 0" % (lo, hi)}
+    sp.close()
+    return res
+
+
+def run_configs(torch, rk, lib, _native, s, blobs, keep):
+    """BASELINE.json configs[1] (6-blob block, latency), configs[2] (4096-blob commitment throughput)
+    and configs[4] (verify_blob_kzg_proof_batch on 4096 blobs), through the C ABI, product calls only."""
+    out = {}
+
+    def timed(f, reps):
+        f()
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter()
+            f()
+            ts.append(time.perf_counter() - t)
+        ts.sort()
+        return ts[0], ts[len(ts) // 2]
+
+    # configs[1]: Cancun-style block, 6 blobs, host buffers, commitment + proof at raiko's challenge
+    six = [blobs[i].cpu().numpy().tobytes() for i in range(6)]
+    best, med = timed(lambda: rk.commit_prove_batch(six, s), 20)
+    res = rk.commit_prove_batch(six, s)
+    for i in range(6):
+        assert res.commitments[i] == keep["c"][i].numpy().tobytes() and res.proofs[i] == keep["p"][i].numpy().tobytes()
+    out["config1_6_blobs_commit_prove_ms"] = {"best": 1e3 * best, "median": 1e3 * med, "buffers": "host (bytes)",
+                                              "note": "BASELINE.json configs[1]; latency of ONE rk_commit_prove_batch call"}
+    best, med = timed(lambda: rk.calc_kzg_proof_commitment(six[0], s), 20)
+    out["single_blob_commitment_ms"] = {"best": 1e3 * best, "median": 1e3 * med}
+
+    # configs[2]: 4096 blobs, commitment only, device resident, with its own roofline inputs
+    n = 4096
+    oc = torch.zeros((n, 48), dtype=torch.uint8, device=blobs.device)
+    ovh = torch.zeros((n, 32), dtype=torch.uint8, device=blobs.device)
+    ost = torch.zeros((n,), dtype=torch.uint8, device=blobs.device)
+
+    def commit():
+        assert lib.rk_commit_batch(s._ctx, _ptr(blobs), n, _ptr(oc), _ptr(ovh), _ptr(ost)) == 0, _native.last_error()
+    commit()
+    s.stats_enable(True)
+    s.stats_reset()
+    best, med = timed(commit, 5)
+    st = s.stats()
+    s.stats_enable(False)
+    assert torch.equal(oc.cpu(), keep["c"][:n]) and int(ost.sum()) == 0
+    out["config2_4096_blobs_commit_only"] = {"blobs_per_s_best": n / best, "blobs_per_s_median": n / med, "ms_best": 1e3 * best,
+                                             "msm_ms_per_call": st["msm_ms"] / 6, "point_adds_per_s": st["msm_point_adds"] / (st["msm_ms"] / 1e3),
+                                             "note": "BASELINE.json configs[2]; rk_commit_batch, inputs resident in HBM; 4096 = 1.73 waves of 2368 one-warp MSMs"}
+
+    # configs[4]: verify_blob_kzg_proof_batch on those 4096 blobs (EIP-4844 challenges, Deneb spec)
+    op = torch.zeros((n, 48), dtype=torch.uint8, device=blobs.device)
+    assert lib.rk_compute_blob_kzg_proof_batch(s._ctx, _ptr(blobs), _ptr(oc), n, _ptr(op), _ptr(ost)) == 0, _native.last_error()
+    craw, praw = oc.cpu().numpy().tobytes(), op.cpu().numpy().tobytes()
+    ok = ctypes.c_int(0)
+
+    def verify(p=praw):
+        assert lib.rk_verify_blob_kzg_proof_batch(s._ctx, _ptr(blobs), ctypes.cast(ctypes.c_char_p(craw), ctypes.c_void_p),
+                                                  ctypes.cast(ctypes.c_char_p(p), ctypes.c_void_p), n, ctypes.byref(ok)) == 0, _native.last_error()
+    best, med = timed(verify, 3)
+    accept = ok.value == 1
+    bad = bytearray(praw)
+    bad[48 * 1234:48 * 1235] = praw[48 * 1235:48 * 1236]
+    verify(bytes(bad))
+    reject = ok.value == 0
+    assert accept and reject, "config 5: accept=%s reject_after_swap=%s" % (accept, reject)
+    out["config4_4096_blobs_verify_batch"] = {"seconds_best": best, "seconds_median": med, "blobs_per_s": n / best, "accept": accept,
+                                              "reject_after_proof_swap": reject,
+                                              "note": "BASELINE.json configs[4]; proofs from rk_compute_blob_kzg_proof_batch; blobs in HBM"}
+    return out
 
 
 _JSON_FD = None

@@ -58,6 +58,9 @@ int rk_kzg_ctx_window_bits(const rk_kzg_ctx* ctx);
 int rk_kzg_ctx_num_devices(const rk_kzg_ctx* ctx);
 /* bytes of HBM held by the window table on each device */
 uint64_t rk_kzg_ctx_table_bytes(const rk_kzg_ctx* ctx);
+/* 1 when window_bits was left to the library and a device lacked the free HBM for c = 15, so a
+ * narrower (slower) table was built; the choice is also reported on stderr at creation time.  */
+int rk_kzg_ctx_window_reduced(const rk_kzg_ctx* ctx);
 
 /* Re-serialise the loaded setup in the reference's own on-disk layouts (what
  * host/src/bin/gen_kzg_settings.rs:8-22 produces).  kind 0 = raw (739 624 B),
@@ -114,6 +117,14 @@ rk_status rk_compute_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, cons
                                      size_t n, uint8_t* out_proofs /* n*48 */,
                                      uint8_t* out_y /* n*32 */, uint8_t* per_blob_status);
 
+/* compute_blob_kzg_proof (Deneb spec; upstream compute_blob_kzg_proof_rust) for n blobs: the
+ * EIP-4844 Fiat-Shamir challenge z_i = hash_to_bls_field(sha256("FSBLOBVERIFY_V1_" | be128(4096)
+ * | blob_i | commitment_i)) -- NOT raiko's evaluation point -- then the proof at z_i.  Produces the
+ * proofs rk_verify_blob_kzg_proof_batch checks (BASELINE.json configs[4]).  commitments: n*48 bytes,
+ * host or device.                                                                             */
+rk_status rk_compute_blob_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments,
+                                          size_t n, uint8_t* out_proofs /* n*48 */, uint8_t* per_blob_status);
+
 /* ---- verification (BASELINE.json configs[4]) -------------------------
  * verify_kzg_proof_rust as the reference's tests use it (eip4844.rs:176-183):
  * e(C - [y]G1 + [z]proof, G2) == e(proof, [s]G2).  *out_ok = 1 accept, 0 reject.  Invalid point
@@ -143,6 +154,13 @@ rk_status rk_verify_blob_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, 
 #define RK_BLOB_DATA_STRIDE 130048
 rk_status rk_decode_blob_data_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_t n, uint8_t* out,
                                     uint32_t* out_len);
+
+/* ---- synthetic input of the measurement contract (bench / test tooling) ------
+ * Writes blobs first_blob .. first_blob + n - 1 of the deterministic family
+ *   fe(b, i) = BE_int(sha256("raiko-kzg-bench-v1" | LE64(seed) | LE32(b) | LE32(i))) mod r
+ * (32-byte big-endian field elements, i = 0..4095) to `out` (n * 131072 bytes, host or device).
+ * The oracle generates the same bytes on the host (tests/kzg_testlib.py::synthetic_blob).        */
+rk_status rk_synth_blobs(rk_kzg_ctx* ctx, uint64_t seed, uint32_t first_blob, size_t n, uint8_t* out);
 
 /* ---- instrumentation ------------------------------------------------------------------ */
 typedef struct {

@@ -28,6 +28,7 @@ SIGNATURES = {
     "rk_kzg_ctx_window_bits": (_I, [_P]),
     "rk_kzg_ctx_num_devices": (_I, [_P]),
     "rk_kzg_ctx_table_bytes": (ctypes.c_uint64, [_P]),
+    "rk_kzg_ctx_window_reduced": (_I, [_P]),
     "rk_kzg_ctx_export_settings": (_I, [_P, _I, _P, ctypes.POINTER(_SZ)]),
     "rk_blob_to_kzg_commitment": (_I, [_P, _P, _SZ, _P]),
     "rk_kzg_to_versioned_hash": (_I, [_P, _P]),
@@ -38,10 +39,12 @@ SIGNATURES = {
     "rk_commit_batch": (_I, [_P, _P, _SZ, _P, _P, _P]),
     "rk_commit_prove_batch": (_I, [_P, _P, _SZ, _P, _P, _P, _P, _P, _P]),
     "rk_compute_kzg_proof_batch": (_I, [_P, _P, _P, _SZ, _P, _P, _P]),
+    "rk_compute_blob_kzg_proof_batch": (_I, [_P, _P, _P, _SZ, _P, _P]),
     "rk_verify_kzg_proof": (_I, [_P, _P, _P, _P, _P, ctypes.POINTER(_I)]),
     "rk_verify_blob_kzg_proof_batch": (_I, [_P, _P, _P, _P, _SZ, ctypes.POINTER(_I)]),
     "rk_verify_kzg_proof_batch": (_I, [_P, _P, _P, _P, _P, _SZ, ctypes.POINTER(_I)]),
     "rk_decode_blob_data_batch": (_I, [_P, _P, _SZ, _P, _P]),
+    "rk_synth_blobs": (_I, [_P, ctypes.c_uint64, ctypes.c_uint32, _SZ, _P]),
     "rk_kzg_stats_enable": (None, [_P, _I]),
     "rk_kzg_stats_reset": (None, [_P]),
     "rk_kzg_stats_get": (None, [_P, ctypes.POINTER(RkKzgStats)]),

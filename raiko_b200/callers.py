@@ -224,6 +224,115 @@ def decode_blob_data(blob: bytes, settings: Optional[KzgSettings] = None) -> byt
 
 
 # ---------------------------------------------------------------------------------------
+# tx-list tail after the codec (lib/src/utils.rs:13-79, 181-193).  Host-only byte work: zlib and
+# the RLP list framing.  What is NOT reproduced is reth's TransactionSigned decoding (signature
+# recovery, per-type field validation): transactions come back as their raw encodings.
+# ---------------------------------------------------------------------------------------
+CALL_DATA_CAPACITY = 4096 * 31                     # utils.rs:84
+
+
+def zlib_decompress_data(data: bytes) -> bytes:
+    """utils.rs:181-186; raises on malformed input (callers use ``unwrap_or_default``)."""
+    import zlib
+    d = zlib.decompressobj()
+    out = d.decompress(bytes(data))
+    if not d.eof:
+        raise ValueError("zlib stream is truncated")
+    return out
+
+
+def zlib_compress_data(data: bytes) -> bytes:
+    """utils.rs:188-193 (the compressed bytes differ from libflate's, the round trip does not)."""
+    import zlib
+    return zlib.compress(bytes(data))
+
+
+def _zlib_or_empty(data: bytes) -> bytes:
+    try:
+        return zlib_decompress_data(data)
+    except Exception:  # noqa: BLE001 -- unwrap_or_default()
+        return b""
+
+
+def get_tx_list(is_taiko: bool, network: str, is_blob_data: bool, tx_list: bytes,
+                settings: Optional[KzgSettings] = None) -> bytes:
+    """utils.rs:27-56: blob data goes through decode_blob_data (GPU codec) then zlib; call data is
+    size-checked before (other Taiko networks) or after (taiko_a7) decompression."""
+    if is_taiko:
+        if is_blob_data:
+            return _zlib_or_empty(decode_blob_data(tx_list, settings))
+        if network == "taiko_a7":
+            out = _zlib_or_empty(tx_list)
+            return out if len(out) <= CALL_DATA_CAPACITY else b""
+        return _zlib_or_empty(tx_list) if len(tx_list) <= CALL_DATA_CAPACITY else b""
+    return _zlib_or_empty(tx_list)
+
+
+def _rlp_item(buf: bytes, pos: int) -> Tuple[int, int, bool]:
+    """(payload start, payload end, is_list) of the RLP item at pos; raises ValueError when malformed."""
+    if pos >= len(buf):
+        raise ValueError("input too short")
+    b = buf[pos]
+    if b < 0x80:
+        return pos, pos + 1, False
+    short, is_list = (0x80, False) if b < 0xC0 else (0xC0, True)
+    if b - short <= 55:
+        start, ln = pos + 1, b - short
+        if not is_list and ln == 1 and start < len(buf) and buf[start] < 0x80:
+            raise ValueError("non-canonical single byte")
+    else:
+        nlen = b - short - 55
+        if pos + 1 + nlen > len(buf) or buf[pos + 1] == 0:
+            raise ValueError("bad length of length")
+        ln = int.from_bytes(buf[pos + 1:pos + 1 + nlen], "big")
+        if ln <= 55:
+            raise ValueError("non-canonical length")
+        start = pos + 1 + nlen
+    if start + ln > len(buf):
+        raise ValueError("input too short")
+    return start, start + ln, is_list
+
+
+def decode_transactions(tx_list: bytes) -> List[bytes]:
+    """utils.rs:13-20: ``Vec::<TransactionSigned>::decode``; ANY failure yields an empty list (the
+    reference then builds an empty block).  Each element is a legacy transaction (an RLP list,
+    returned with its header) or a typed one (an RLP string ``type || payload``, returned without
+    the string header, i.e. the EIP-2718 envelope)."""
+    try:
+        start, end, is_list = _rlp_item(tx_list, 0)
+        if not is_list:
+            raise ValueError("not a list")
+        txs, pos = [], start
+        while pos < end:
+            s, e, lst = _rlp_item(tx_list, pos)
+            if e > end:
+                raise ValueError("item overruns the list")
+            if lst:
+                txs.append(bytes(tx_list[pos:e]))
+            else:
+                env = bytes(tx_list[s:e])
+                if not env or env[0] > 0x7F:
+                    raise ValueError("bad typed-transaction envelope")
+                _s2, e2, l2 = _rlp_item(env, 1)
+                if not l2 or e2 != len(env):
+                    raise ValueError("typed transaction payload is not one list")
+                txs.append(env)
+            pos = e
+        return txs
+    except (ValueError, IndexError):
+        return []
+
+
+def generate_transactions(is_taiko: bool, network: str, is_blob_data: bool, tx_list: bytes,
+                          anchor_tx: Optional[bytes] = None, settings: Optional[KzgSettings] = None) -> List[bytes]:
+    """utils.rs:58-73: tx list from the raw data posted on chain, anchor transaction first."""
+    txs = decode_transactions(get_tx_list(is_taiko, network, is_blob_data, tx_list, settings))
+    if anchor_tx is not None:
+        txs.insert(0, bytes(anchor_tx))
+    return txs
+
+
+# ---------------------------------------------------------------------------------------
 # run_prover tail (core/src/interfaces.rs:207-219)
 # ---------------------------------------------------------------------------------------
 def kzg_proof_hex(tx_data: bytes, blob_commitment: Optional[bytes], settings: Optional[KzgSettings] = None) -> Optional[str]:

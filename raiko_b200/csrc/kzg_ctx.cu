@@ -44,6 +44,27 @@ rk_status fail(rk_status st, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                 \
     } while (0)
 
+// Every extern "C" entry point that touches a device restores the caller's current device on
+// exit: a PyTorch (or any other CUDA) host thread must not find its device switched under it.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+struct DevBuf {          // RAII for device scratch that lives for one call: freed on every exit path
+    std::vector<void*> ptrs;
+    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> cudaError_t alloc(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T));
+        if (e == cudaSuccess) { ptrs.push_back(p); *out = (T*)p; }
+        return e;
+    }
+};
+
 constexpr size_t RAW_LEN = 739624, BINCODE_LEN = 1001905;
 constexpr size_t RAW_ROOTS = 8, RAW_G1 = 131080, RAW_G2 = 720904;
 constexpr size_t BC_EXPANDED = 40, BC_REVERSE = 131152, BC_ROOTS = 262264, BC_G1 = 393344, BC_G2 = 983176;
@@ -79,6 +100,7 @@ struct ChunkSlot {
     G1Xyzz* d_partials = nullptr;   // one XYZZ partial sum per MSM warp: max(chunk, 128 * 32)
     uint8_t* d_out = nullptr;       // per blob: C48 | vh32 | x32 | y32 | proof48 | hash32 | status1(+pad)
     uint8_t* d_zin = nullptr;       // chunk * 32 (compute_kzg_proof inputs)
+    uint8_t* d_cin = nullptr;       // chunk * 48 (compute_blob_kzg_proof inputs)
     Fr* d_inv = nullptr;            // chunk * 4096 Fr: batch-inversion scratch of k_fr_eval_quot
     uint32_t* d_bad = nullptr;      // chunk
     uint8_t* h_out = nullptr;       // pinned mirror of d_out
@@ -117,6 +139,8 @@ struct DeviceCtx {
     int aff_warps = MSM_AFF_THREADS / 32;      // warps per CTA of the affine kernel (one CTA per SM)
     int aff_min_entries = 8 * MSM_AFF_MAX_K;   // per-lane table entries below which k_msm is used
     int max_splits_log2 = 7;                   // test knob: 0 forces one warp per blob
+    bool window_reduced = false;               // auto-selection had to go below c = 15 for lack of free HBM
+    bool wave_tail = true;                     // wave-aware chunk schedule and tail split (RAIKO_KZG_WAVE_TAIL=0: off)
     uint32_t* aff_scratch = nullptr;       // sm_count x chains x 39 words x 256 threads
     uint32_t recode_h[8] = {0};
     // stats
@@ -192,7 +216,7 @@ void free_device(DeviceCtx* d) {
     cudaSetDevice(d->dev);
     for (auto& s : d->slot) {
         cudaFree(s.d_blobs); cudaFree(s.d_q); cudaFree(s.d_partials); cudaFree(s.d_out);
-        cudaFree(s.d_zin); cudaFree(s.d_bad); cudaFree(s.d_inv);
+        cudaFree(s.d_zin); cudaFree(s.d_cin); cudaFree(s.d_bad); cudaFree(s.d_inv);
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.ev_in) cudaEventDestroy(s.ev_in);
         if (s.ev_sha) cudaEventDestroy(s.ev_sha);
@@ -211,8 +235,9 @@ void free_device(DeviceCtx* d) {
 // big-endian G2 coordinates on the host.
 rk_status load_setup(DeviceCtx* d, const uint8_t* data, size_t len, std::vector<uint8_t>* g2_be) {
     CUDA_TRY(cudaMalloc(&d->g1_aff, sizeof(G1Affine) * NPTS));
+    DevBuf buf;                                   // scratch is released on every return below
     int* d_err = nullptr;
-    CUDA_TRY(cudaMalloc(&d_err, sizeof(int)));
+    CUDA_TRY(buf.alloc(&d_err, 1));
     CUDA_TRY(cudaMemset(d_err, 0, sizeof(int)));
     uint8_t* d_in = nullptr;
     size_t g1_off = 0, g2_off = 0;
@@ -236,15 +261,13 @@ rk_status load_setup(DeviceCtx* d, const uint8_t* data, size_t len, std::vector<
         return fail(RK_ERR_BAD_SETTINGS, "unrecognised settings image (%zu bytes)", len);
     }
     const size_t g1_bytes = ref_format ? 144ull * NPTS : 48ull * NPTS;
-    CUDA_TRY(cudaMalloc(&d_in, g1_bytes));
+    CUDA_TRY(buf.alloc(&d_in, g1_bytes));
     CUDA_TRY(cudaMemcpy(d_in, data + g1_off, g1_bytes, cudaMemcpyHostToDevice));
     if (ref_format) launch_k_setup_from_ref(NPTS / 64, 64, 0, 0, d_in, NPTS, d->g1_aff, d_err);
     else launch_k_setup_decompress(NPTS / 64, 64, 0, 0, d_in, NPTS, d->g1_aff, d_err);
     CUDA_TRY(cudaGetLastError());
     int err = 0;
     CUDA_TRY(cudaMemcpy(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(d_in);
-    cudaFree(d_err);
     if (err) return fail(RK_ERR_BAD_SETTINGS, "setup G1 point %d is not a valid affine curve point", err - 1);
     if (g2_be) {
         g2_be->resize(192 * N_G2);
@@ -253,13 +276,12 @@ rk_status load_setup(DeviceCtx* d, const uint8_t* data, size_t len, std::vector<
         } else {
             // 65 x (X.c0 X.c1 Y.c0 Y.c1 Z.c0 Z.c1) Montgomery limbs -> big-endian canonical x, y
             uint8_t *d_g2 = nullptr, *d_o = nullptr;
-            CUDA_TRY(cudaMalloc(&d_g2, 288 * N_G2));
-            CUDA_TRY(cudaMalloc(&d_o, 288 * N_G2));
+            CUDA_TRY(buf.alloc(&d_g2, 288 * N_G2));
+            CUDA_TRY(buf.alloc(&d_o, 288 * N_G2));
             CUDA_TRY(cudaMemcpy(d_g2, data + g2_off, 288 * N_G2, cudaMemcpyHostToDevice));
             launch_k_fp_ref_to_be((6 * N_G2 + 63) / 64, 64, 0, 0, d_g2, 6 * N_G2, d_o);
             std::vector<uint8_t> tmp(288 * N_G2);
             CUDA_TRY(cudaMemcpy(tmp.data(), d_o, tmp.size(), cudaMemcpyDeviceToHost));
-            cudaFree(d_g2); cudaFree(d_o);
             for (int i = 0; i < N_G2; i++) {
                 const uint8_t* p = tmp.data() + 288 * i;
                 // Z must be (1, 0)
@@ -282,16 +304,17 @@ rk_status build_table(DeviceCtx* d) {
     const int chains = NPTS * g.W;
     G1Xyzz *bases = nullptr, *state = nullptr, *tmp = nullptr;
     G1Affine* bases_aff = nullptr;
-    CUDA_TRY(cudaMalloc(&bases, sizeof(G1Xyzz) * chains));
-    CUDA_TRY(cudaMalloc(&bases_aff, sizeof(G1Affine) * chains));
-    CUDA_TRY(cudaMalloc(&state, sizeof(G1Xyzz) * chains));
+    DevBuf buf;
+    CUDA_TRY(buf.alloc(&bases, (size_t)chains));
+    CUDA_TRY(buf.alloc(&bases_aff, (size_t)chains));
+    CUDA_TRY(buf.alloc(&state, (size_t)chains));
     launch_k_table_bases(NPTS / 64, 64, 0, 0, d->g1_aff, g, bases);
     launch_k_table_bases_affine((chains / 16 + 63) / 64, 64, 0, 0, bases, chains, bases_aff);
     CUDA_TRY(cudaGetLastError());
     const uint32_t emax = std::max(g.half, g.top_entries);
     int D = 256;
     while ((uint32_t)D > emax && D > TABLE_NORM_G) D >>= 1;
-    CUDA_TRY(cudaMalloc(&tmp, sizeof(G1Xyzz) * (size_t)chains * D));
+    CUDA_TRY(buf.alloc(&tmp, (size_t)chains * D));
     for (uint32_t d0 = 1; d0 <= emax; d0 += D) {
         launch_k_table_chain((chains + 127) / 128, 128, 0, 0, bases_aff, g, d0, D, state, tmp);
         const long long groups = (long long)chains * (D / TABLE_NORM_G);
@@ -299,7 +322,6 @@ rk_status build_table(DeviceCtx* d) {
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
-    cudaFree(bases); cudaFree(bases_aff); cudaFree(state); cudaFree(tmp);
     return RK_OK;
 }
 
@@ -321,6 +343,7 @@ rk_status alloc_slots(DeviceCtx* d) {
     d->aff_min_entries = 8 * d->aff_chains;
     if (const char* e = getenv("RAIKO_KZG_AFFINE_MIN_ENTRIES")) d->aff_min_entries = std::max(1, atoi(e));
     if (const char* e = getenv("RAIKO_KZG_MAX_SPLITS_LOG2")) d->max_splits_log2 = std::min(7, std::max(0, atoi(e)));
+    if (const char* e = getenv("RAIKO_KZG_WAVE_TAIL")) d->wave_tail = atoi(e) != 0;
     if (d->msm_affine) {
         CUDA_TRY(configure_k_msm_affine());
         CUDA_TRY(cudaMalloc(&d->aff_scratch, (size_t)d->sm_count * d->aff_chains * AFF_WORDS * (32 * d->aff_warps) * sizeof(uint32_t)));
@@ -332,10 +355,12 @@ rk_status alloc_slots(DeviceCtx* d) {
         }
     }
     for (auto& s : d->slot) {
+        CUDA_TRY(cudaMalloc(&s.d_blobs, (size_t)d->chunk * BLOB_BYTES));   // staging of host-pointer input
         CUDA_TRY(cudaMalloc(&s.d_q, (size_t)d->chunk * BLOB_BYTES));
         CUDA_TRY(cudaMalloc(&s.d_partials, sizeof(G1Xyzz) * (size_t)d->max_partials));
         CUDA_TRY(cudaMalloc(&s.d_out, (size_t)d->chunk * OUT_STRIDE + d->chunk));
         CUDA_TRY(cudaMalloc(&s.d_zin, (size_t)d->chunk * 32));
+        CUDA_TRY(cudaMalloc(&s.d_cin, (size_t)d->chunk * 48));
         CUDA_TRY(cudaMalloc(&s.d_inv, sizeof(Fr) * (size_t)d->chunk * NPTS));
         CUDA_TRY(cudaMalloc(&s.d_bad, sizeof(uint32_t) * d->chunk));
         CUDA_TRY(cudaMallocHost(&s.h_out, (size_t)d->chunk * OUT_STRIDE + d->chunk));
@@ -370,6 +395,14 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
             double need = (double)NPTS * g.per_point * sizeof(TableEntry) + 8e9;   // table + build scratch + chunk buffers
             if (need < 0.80 * (double)free_b) break;
         }
+        if (c < 15) {
+            // Not silent: a narrower window means more additions per MSM (W = ceil(255 / c)) and
+            // proportionally lower throughput (DESIGN.md section 8 lists c = 13 / 14).
+            d->window_reduced = true;
+            fprintf(stderr, "raiko_kzg: GPU %d has %.1f GB free of %.1f GB: window table narrowed to c = %d (%d additions per scalar "
+                            "instead of 17); free HBM or pass window_bits explicitly\n",
+                    d->dev, free_b / 1e9, total_b / 1e9, c, (255 + c - 1) / c);
+        }
     }
     if (c < 4 || c > 15) return fail(RK_ERR_ARG, "window_bits %d outside 4..15", c);
     d->geom = make_geom(c);
@@ -394,7 +427,8 @@ rk_status init_device(DeviceCtx* d, const uint8_t* settings, size_t len, int win
 // Batch pipeline on one device
 // ----------------------------------------------------------------------------------------
 enum BatchMode { MODE_COMMIT = 0, MODE_COMMIT_PROVE = 1, MODE_PROOF_AT_Z = 2, MODE_EVAL_ONLY = 3, MODE_POINT_ONLY = 4,
-                 MODE_PROVE_VH = 5 /* calc_kzg_proof: challenge from (blob, vh), then the proof */ };
+                 MODE_PROVE_VH = 5 /* calc_kzg_proof: challenge from (blob, vh), then the proof */,
+                 MODE_BLOB_PROOF = 6 /* compute_blob_kzg_proof: EIP-4844 challenge from (blob, commitment), then the proof */ };
 
 struct BatchArgs {
     BatchMode mode;
@@ -402,6 +436,7 @@ struct BatchArgs {
     bool blobs_on_device;
     const uint8_t* zs;           // MODE_PROOF_AT_Z: host, n*32
     const uint8_t* vhs;          // MODE_EVAL_ONLY / MODE_POINT_ONLY / MODE_PROVE_VH: host, n*32
+    const uint8_t* cins;         // MODE_BLOB_PROOF: commitments, host or device, n*48
     size_t n;
     uint8_t *out_c, *out_vh, *out_x, *out_y, *out_proof, *status;   // host or device, may be null
     bool outs_on_device;
@@ -410,6 +445,7 @@ struct BatchArgs {
 struct MsmPlan {
     int splits_log2;
     bool affine;
+    double cost;      // estimated duration, in units of one XYZZ addition per lane at 8 warps/SM
 };
 
 MsmPlan plan_msm(const DeviceCtx* d, size_t nblobs) {
@@ -420,7 +456,7 @@ MsmPlan plan_msm(const DeviceCtx* d, size_t nblobs) {
     // shuffle tree; k_msm_affine runs 16 warps/SM, each addition 1.36 units, plus ~150 for the
     // chain sums and the tree -- so it wins once a lane owns a few hundred table entries.
     const double adds_per_lane = (double)NPTS * d->geom.W / 32.0;
-    MsmPlan best{0, false};
+    MsmPlan best{0, false, 1e300};
     double best_t = 1e300;
     for (int lg = 0; lg <= d->max_splits_log2; lg++) {
         if ((nblobs << lg) > (size_t)d->max_partials) break;          // one XYZZ partial per warp
@@ -429,23 +465,56 @@ MsmPlan plan_msm(const DeviceCtx* d, size_t nblobs) {
         const double t_x = std::ceil(warps / ((double)d->sm_count * d->warps_per_sm)) * (per_lane + 8.0);
         const int entries = ((NPTS >> lg) >> 5) * d->geom.W;
         const bool eligible = d->msm_affine && d->aff_scratch && entries >= d->aff_min_entries;
-        if (!(eligible && d->msm_affine == 2) && t_x < best_t * 0.999) { best_t = t_x; best = {lg, false}; }
+        if (!(eligible && d->msm_affine == 2) && t_x < best_t * 0.999) { best_t = t_x; best = {lg, false, t_x}; }
         if (eligible) {
             const double t_a = std::ceil(warps / ((double)d->sm_count * d->aff_warps)) * (1.36 * per_lane + 150.0);
-            if (t_a < best_t * 0.999) { best_t = t_a; best = {lg, true}; }
+            if (t_a < best_t * 0.999) { best_t = t_a; best = {lg, true, t_a}; }
         }
     }
     return best;
 }
 
-void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint32_t* bad, int* splits_out) {
-    const MsmPlan plan = plan_msm(d, (size_t)n);
-    const long long warps = (long long)n << plan.splits_log2;
+// One MSM launch over blobs [first, first + count) of a chunk: 1 << splits_log2 warps per blob,
+// its XYZZ partial sums at partials[part_off ...).
+struct MsmSeg {
+    int first, count, splits_log2;
+    size_t part_off;
+    bool affine;
+};
+
+// Wave-aware launch plan of one chunk.  Every warp of an MSM launch does the same work, so a
+// launch runs in whole waves of resident warps and a chunk that is not a whole number of waves
+// idles SMs in its last one (8192 blobs = 3.46 waves of 2368 cost 4 wave times).  A chunk that
+// the planner would run one warp per blob is therefore cut into its whole waves plus a
+// remainder, and the remainder is planned on its own: it gets the split that fills the machine
+// (1088 blobs -> 2 warps per blob = 0.92 wave of half-size work), so 3.46 waves cost 3.5.
+int plan_chunk(const DeviceCtx* d, int n, MsmSeg (&seg)[2]) {
+    const MsmPlan whole = plan_msm(d, (size_t)n);
+    seg[0] = {0, n, whole.splits_log2, 0, whole.affine};
+    // candidate: whole waves of the one-warp-per-blob affine kernel + a separately planned remainder
+    const int wave = d->sm_count * d->aff_warps;
+    const int entries = (NPTS >> 5) * d->geom.W;
+    const bool affine_ok = d->msm_affine && d->aff_scratch && entries >= d->aff_min_entries;
+    if (!d->wave_tail || !affine_ok || n <= wave || n % wave == 0) return 1;
+    const int body = n / wave * wave;
+    const MsmPlan rest = plan_msm(d, (size_t)(n - body));
+    const double t_body = (double)(body / wave) * (1.36 * (double)NPTS * d->geom.W / 32.0 + 150.0);
+    if (t_body + rest.cost >= 0.98 * whole.cost) return 1;          // nothing to gain: keep one launch
+    seg[0] = {0, body, 0, 0, true};
+    seg[1] = {body, n - body, rest.splits_log2, (size_t)body, rest.affine};
+    return 2;
+}
+
+void launch_msm_seg(DeviceCtx* d, const uint8_t* scalars, ChunkSlot& s, uint32_t* bad, const MsmSeg& g) {
+    const int n = g.count;
+    const uint8_t* sc = scalars + (size_t)g.first * BLOB_BYTES;
+    uint32_t* bd = bad ? bad + g.first : nullptr;
+    const long long warps = (long long)n << g.splits_log2;
     timer_begin(d, d->s_main, T_MSM);
-    if (plan.affine) {
+    if (g.affine) {
         MsmAffParams q;
-        q.table = d->table; q.g = d->geom; q.scalars = scalars; q.nblobs = n; q.splits_log2 = plan.splits_log2;
-        q.partials = s.d_partials; q.bad = bad; q.scratch = d->aff_scratch; q.K = d->aff_chains;
+        q.table = d->table; q.g = d->geom; q.scalars = sc; q.nblobs = n; q.splits_log2 = g.splits_log2;
+        q.partials = s.d_partials + g.part_off; q.bad = bd; q.scratch = d->aff_scratch; q.K = d->aff_chains;
         const int wpc = d->aff_warps, threads = 32 * wpc;
         q.ngroups = (int)((warps + wpc - 1) / wpc);
         memcpy(q.H, d->recode_h, sizeof q.H);
@@ -455,21 +524,67 @@ void launch_msm(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint3
         d->stats.msm_affine_point_adds += (uint64_t)n * NPTS * d->geom.W;
     } else {
         MsmParams p;
-        p.table = d->table; p.g = d->geom; p.scalars = scalars; p.nblobs = n;
-        p.splits_log2 = plan.splits_log2;
-        p.partials = s.d_partials; p.bad = bad;
+        p.table = d->table; p.g = d->geom; p.scalars = sc; p.nblobs = n;
+        p.splits_log2 = g.splits_log2;
+        p.partials = s.d_partials + g.part_off; p.bad = bd;
         launch_k_msm((unsigned)((warps + 7) / 8), 256, 0, d->s_main, p);
     }
     timer_end(d, d->s_main);
     d->stats.msm_point_adds += (uint64_t)n * NPTS * d->geom.W;
-    *splits_out = 1 << plan.splits_log2;
+}
+
+// MSM over the chunk's scalars followed by the reduction of the partial sums to compressed
+// points at out_g1 (+ versioned hashes at out_vh when given), segment by segment.
+void msm_and_finalize(DeviceCtx* d, const uint8_t* scalars, int n, ChunkSlot& s, uint32_t* bad_msm, uint8_t* out_g1,
+                      uint8_t* out_vh, uint8_t* o_stat) {
+    MsmSeg seg[2];
+    const int nseg = plan_chunk(d, n, seg);
+    for (int i = 0; i < nseg; i++) launch_msm_seg(d, scalars, s, bad_msm, seg[i]);
+    timer_begin(d, d->s_main, T_FIN);
+    for (int i = 0; i < nseg; i++) {
+        const MsmSeg& g = seg[i];
+        const int splits = 1 << g.splits_log2;
+        const G1Xyzz* part = s.d_partials + g.part_off;
+        uint8_t* og = out_g1 + (size_t)g.first * OUT_STRIDE;
+        uint8_t* ov = out_vh ? out_vh + (size_t)g.first * OUT_STRIDE : nullptr;
+        if (splits >= 8) launch_k_finalize_warp(g.count, 32, 0, d->s_main, part, splits, g.count, s.d_bad + g.first, og, ov, o_stat + g.first, OUT_STRIDE);
+        else launch_k_finalize((g.count + 31) / 32, 32, 0, d->s_main, part, splits, g.count, s.d_bad + g.first, og, ov, o_stat + g.first, OUT_STRIDE);
+        if (i) d->stats.total_launches++;
+    }
+    timer_end(d, d->s_main);
+}
+
+// Chunk schedule of one shard: whole multiples of the one-warp-per-blob wave wherever possible,
+// a one-wave first chunk for host input (compute starts after 310 MB of H2D instead of 620 MB),
+// and whatever is left as the last chunk (plan_chunk splits its partial wave).
+std::vector<size_t> chunk_schedule(const DeviceCtx* d, size_t n, bool host_input) {
+    std::vector<size_t> sizes;
+    const size_t chunk = (size_t)d->chunk;
+    const size_t wave = (size_t)d->sm_count * (d->msm_affine ? d->aff_warps : d->warps_per_sm);
+    size_t left = n;
+    if (host_input && d->wave_tail && wave < chunk && n > wave) { sizes.push_back(wave); left -= wave; }
+    while (left > 0) { const size_t c = std::min(chunk, left); sizes.push_back(c); left -= c; }
+    return sizes;
 }
 
 rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
     std::lock_guard<std::mutex> lock(d->mu);
     CUDA_TRY(cudaSetDevice(d->dev));
     const size_t chunk = (size_t)d->chunk;
-    const size_t nchunks = (a.n + chunk - 1) / chunk;
+    // Whatever way this function is left, no slot stays marked busy and no copy into the caller's
+    // arrays is still in flight: a failed call must not leak state into the next one.
+    struct SlotReset {
+        DeviceCtx* d;
+        bool ok = false;
+        ~SlotReset() {
+            if (ok) return;
+            cudaStreamSynchronize(d->s_in); cudaStreamSynchronize(d->s_main);
+            cudaStreamSynchronize(d->s_sha); cudaStreamSynchronize(d->s_out);
+            cudaGetLastError();
+            for (auto& s : d->slot) { s.busy = false; s.count = 0; }
+            timers_collect(d);
+        }
+    } reset{d};
     auto drain = [&](ChunkSlot& s) -> rk_status {
         if (!s.busy) return RK_OK;
         CUDA_TRY(cudaEventSynchronize(s.ev_out));
@@ -489,20 +604,19 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
         return RK_OK;
     };
 
-    for (size_t ci = 0; ci < nchunks; ci++) {
+    const std::vector<size_t> sizes = chunk_schedule(d, a.n, !a.blobs_on_device);
+    size_t first = 0;
+    for (size_t ci = 0; ci < sizes.size(); ci++) {
         ChunkSlot& s = d->slot[ci & 1];
         rk_status st = drain(s);
         if (st != RK_OK) return st;
-        const size_t first = ci * chunk;
-        const int cnt = (int)std::min(chunk, a.n - first);
-        s.first = first; s.count = (size_t)cnt; s.busy = true;
+        const int cnt = (int)sizes[ci];
 
         // ---- input ---------------------------------------------------------------------
         const uint8_t* d_blobs;
         if (a.blobs_on_device) {
             d_blobs = a.blobs + first * BLOB_BYTES;
         } else {
-            if (!s.d_blobs) CUDA_TRY(cudaMalloc(&s.d_blobs, chunk * BLOB_BYTES));
             CUDA_TRY(cudaMemcpyAsync(s.d_blobs, a.blobs + first * BLOB_BYTES, (size_t)cnt * BLOB_BYTES,
                                      cudaMemcpyHostToDevice, d->s_in));
             d->stats.h2d_bytes += (uint64_t)cnt * BLOB_BYTES;
@@ -511,6 +625,10 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
         if (a.mode == MODE_PROOF_AT_Z) {
             CUDA_TRY(cudaMemcpyAsync(s.d_zin, a.zs + 32 * first, 32 * (size_t)cnt, cudaMemcpyHostToDevice, d->s_in));
             d->stats.h2d_bytes += 32ull * cnt;
+        }
+        if (a.mode == MODE_BLOB_PROOF) {
+            CUDA_TRY(cudaMemcpyAsync(s.d_cin, a.cins + 48 * first, 48 * (size_t)cnt, cudaMemcpyDefault, d->s_in));
+            d->stats.h2d_bytes += 48ull * cnt;
         }
         uint8_t* o = s.d_out;
         uint8_t* o_stat = s.d_out + chunk * OUT_STRIDE;
@@ -537,24 +655,22 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             timer_end(d, hs);
             CUDA_TRY(cudaEventRecord(s.ev_sha, hs));
         }
-        int splits = 1;
         // ---- commitment ------------------------------------------------------------------
-        if (a.mode == MODE_COMMIT || a.mode == MODE_COMMIT_PROVE) {
-            launch_msm(d, d_blobs, cnt, s, s.d_bad, &splits);
-            timer_begin(d, d->s_main, T_FIN);
-            if (splits >= 8) launch_k_finalize_warp(cnt, 32, 0, d->s_main, s.d_partials, splits, cnt, s.d_bad, o + OFF_C, o + OFF_VH, o_stat, OUT_STRIDE);
-            else launch_k_finalize((cnt + 31) / 32, 32, 0, d->s_main, s.d_partials, splits, cnt, s.d_bad, o + OFF_C, o + OFF_VH,
-                                                              o_stat, OUT_STRIDE);
-            timer_end(d, d->s_main);
-        }
+        if (a.mode == MODE_COMMIT || a.mode == MODE_COMMIT_PROVE)
+            msm_and_finalize(d, d_blobs, cnt, s, s.d_bad, o + OFF_C, o + OFF_VH, o_stat);
         // ---- evaluation / quotient -------------------------------------------------------
         if (a.mode != MODE_COMMIT) {
             if (need_hash) CUDA_TRY(cudaStreamWaitEvent(d->s_main, s.ev_sha, 0));
+            if (a.mode == MODE_BLOB_PROOF) {       // z = compute_challenge(blob, commitment), Deneb spec
+                timer_begin(d, d->s_main, T_SHA);
+                launch_k_sha_fs_challenge((cnt + 31) / 32, 32, 0, d->s_main, d_blobs, s.d_cin, cnt, s.d_zin);
+                timer_end(d, d->s_main);
+            }
             FrParams fp;
             fp.blobs = d_blobs; fp.roots_brp = d->roots;
             fp.blob_hash = o + OFF_HASH; fp.vh = o + OFF_VH; fp.z_in = s.d_zin;
-            fp.mode = (a.mode == MODE_PROOF_AT_Z) ? 1 : 0;
-            fp.want_quotient = (a.mode == MODE_COMMIT_PROVE || a.mode == MODE_PROOF_AT_Z || a.mode == MODE_PROVE_VH) ? 1 : 0;
+            fp.mode = (a.mode == MODE_PROOF_AT_Z || a.mode == MODE_BLOB_PROOF) ? 1 : 0;
+            fp.want_quotient = (a.mode == MODE_COMMIT_PROVE || a.mode == MODE_PROOF_AT_Z || a.mode == MODE_PROVE_VH || a.mode == MODE_BLOB_PROOF) ? 1 : 0;
             fp.eval = (a.mode == MODE_POINT_ONLY) ? 0 : 1;
             fp.nblobs = cnt; fp.out_x = o + OFF_X; fp.out_y = o + OFF_Y; fp.q_out = s.d_q; fp.bad = s.d_bad;
             fp.out_stride = OUT_STRIDE;
@@ -562,19 +678,9 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             timer_begin(d, d->s_main, T_FR);
             launch_k_fr_eval_quot(cnt, FR_THREADS, FR_SMEM_BYTES, d->s_main, fp);
             timer_end(d, d->s_main);
-            if (fp.want_quotient) {
-                launch_msm(d, s.d_q, cnt, s, nullptr, &splits);
-                timer_begin(d, d->s_main, T_FIN);
-                if (splits >= 8) launch_k_finalize_warp(cnt, 32, 0, d->s_main, s.d_partials, splits, cnt, s.d_bad, o + OFF_PROOF, nullptr, o_stat, OUT_STRIDE);
-                else launch_k_finalize((cnt + 31) / 32, 32, 0, d->s_main, s.d_partials, splits, cnt, s.d_bad, o + OFF_PROOF, nullptr,
-                                                                  o_stat, OUT_STRIDE);
-                timer_end(d, d->s_main);
-                launch_k_status_only((cnt + 127) / 128, 128, 0, d->s_main, s.d_bad, cnt, o, o_stat, OUT_STRIDE, OFF_HASH);
-                d->stats.total_launches++;
-            } else {
-                launch_k_status_only((cnt + 127) / 128, 128, 0, d->s_main, s.d_bad, cnt, o, o_stat, OUT_STRIDE, OFF_HASH);
-                d->stats.total_launches++;
-            }
+            if (fp.want_quotient) msm_and_finalize(d, s.d_q, cnt, s, nullptr, o + OFF_PROOF, nullptr, o_stat);
+            launch_k_status_only((cnt + 127) / 128, 128, 0, d->s_main, s.d_bad, cnt, o, o_stat, OUT_STRIDE, OFF_HASH);
+            d->stats.total_launches++;
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(s.ev_done, d->s_main));
@@ -598,6 +704,9 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             d->stats.d2h_bytes += (uint64_t)cnt * (OUT_STRIDE + 1);
         }
         CUDA_TRY(cudaEventRecord(s.ev_out, d->s_out));
+        // only now does the slot hold results that drain() may copy out
+        s.first = first; s.count = (size_t)cnt; s.busy = true;
+        first += (size_t)cnt;
     }
     for (auto& s : d->slot) {
         rk_status st = drain(s);
@@ -607,25 +716,43 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
     CUDA_TRY(cudaStreamSynchronize(d->s_sha));
     CUDA_TRY(cudaStreamSynchronize(d->s_out));
     timers_collect(d);
+    reset.ok = true;
     return RK_OK;
 }
 
-bool is_device_ptr(const void* p) {
-    if (!p) return false;
+// Device that owns `p`, or -1 for host memory (pageable or pinned) and NULL.
+int device_of_ptr(const void* p) {
+    if (!p) return -1;
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return attr.device;
+    return -1;
+}
+bool is_device_ptr(const void* p) { return device_of_ptr(p) >= 0; }
+// A device pointer handed to this library must live on the context's first device, as the header
+// promises; anything else would be read through peer access at best and fault at worst.
+rk_status check_ptr_device(const rk_kzg_ctx* ctx, const void* p, const char* what) {
+    const int dev = device_of_ptr(p);
+    if (dev >= 0 && dev != ctx->devs[0]->dev)
+        return fail(RK_ERR_ARG, "%s is device memory of GPU %d but the context's first device is GPU %d", what, dev, ctx->devs[0]->dev);
+    return RK_OK;
 }
 
 rk_status run_batch(rk_kzg_ctx* ctx, BatchArgs a) {
     if (!ctx) return fail(RK_ERR_ARG, "null context");
     if (a.n == 0) return RK_OK;
     if (!a.blobs) return fail(RK_ERR_ARG, "null blobs pointer");
+    DeviceGuard dg;
     cudaSetDevice(ctx->devs[0]->dev);
     a.blobs_on_device = is_device_ptr(a.blobs);
+    rk_status pst = check_ptr_device(ctx, a.blobs, "blobs");
+    if (pst != RK_OK) return pst;
     uint8_t* outs[6] = {a.out_c, a.out_vh, a.out_x, a.out_y, a.out_proof, a.status};
     int n_dev_out = 0, n_out = 0;
-    for (uint8_t* p : outs) if (p) { n_out++; n_dev_out += is_device_ptr(p) ? 1 : 0; }
+    for (uint8_t* p : outs) if (p) {
+        n_out++; n_dev_out += is_device_ptr(p) ? 1 : 0;
+        if ((pst = check_ptr_device(ctx, p, "an output array")) != RK_OK) return pst;
+    }
     if (n_dev_out != 0 && n_dev_out != n_out) return fail(RK_ERR_ARG, "outputs must be all host or all device pointers");
     a.outs_on_device = n_dev_out != 0;
     if ((a.blobs_on_device || a.outs_on_device) && ctx->devs.size() != 1)
@@ -644,6 +771,7 @@ rk_status run_batch(rk_kzg_ctx* ctx, BatchArgs a) {
         s.n = hi - lo;
         if (a.zs) s.zs = a.zs + 32 * lo;
         if (a.vhs) s.vhs = a.vhs + 32 * lo;
+        if (a.cins) s.cins = a.cins + 48 * lo;
         if (a.out_c) s.out_c = a.out_c + 48 * lo;
         if (a.out_vh) s.out_vh = a.out_vh + 32 * lo;
         if (a.out_x) s.out_x = a.out_x + 32 * lo;
@@ -662,17 +790,6 @@ rk_status run_batch(rk_kzg_ctx* ctx, BatchArgs a) {
 // Verification (single device: ctx device 0)
 // ----------------------------------------------------------------------------------------
 constexpr size_t VERIFY_MAX_N = 16384;
-
-struct DevBuf {          // RAII for the scratch of one verification call
-    std::vector<void*> ptrs;
-    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
-    template <class T> cudaError_t alloc(T** out, size_t count) {
-        void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T));
-        if (e == cudaSuccess) { ptrs.push_back(p); *out = (T*)p; }
-        return e;
-    }
-};
 
 // d_c, d_p: n x 48 compressed; d_z, d_y: n x 32 big-endian canonical (all on the device).
 rk_status verify_core(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, int n, const uint8_t* d_c, const uint8_t* d_p,
@@ -729,10 +846,15 @@ rk_status verify_core(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, int n, const u
 rk_status verify_blob_batch_device(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs,
                                    size_t n, int* out_ok) {
     DeviceCtx* d = ctx->devs[0];
+    DeviceGuard dg;
     std::lock_guard<std::mutex> lock(d->mu);
     CUDA_TRY(cudaSetDevice(d->dev));
     const bool blobs_dev = is_device_ptr(blobs);
     if (blobs_dev && ((uintptr_t)blobs & 15)) return fail(RK_ERR_ARG, "device blob pointer must be 16-byte aligned");
+    for (const void* p : {(const void*)blobs, (const void*)commitments, (const void*)proofs}) {
+        rk_status pst = check_ptr_device(ctx, p, "an input array");
+        if (pst != RK_OK) return pst;
+    }
     DevBuf buf;
     uint8_t *d_c = nullptr, *d_p = nullptr, *d_z = nullptr, *d_y = nullptr;
     uint32_t* d_bad = nullptr;
@@ -750,7 +872,6 @@ rk_status verify_blob_batch_device(rk_kzg_ctx* ctx, const uint8_t* blobs, const 
         if (blobs_dev) {
             d_blobs = blobs + first * BLOB_BYTES;
         } else {
-            if (!s.d_blobs) CUDA_TRY(cudaMalloc(&s.d_blobs, chunk * BLOB_BYTES));
             if (ci >= 2) CUDA_TRY(cudaEventSynchronize(s.ev_done));        // slot free again?
             CUDA_TRY(cudaMemcpyAsync(s.d_blobs, blobs + first * BLOB_BYTES, (size_t)cnt * BLOB_BYTES, cudaMemcpyHostToDevice, d->s_in));
             CUDA_TRY(cudaEventRecord(s.ev_in, d->s_in));
@@ -859,6 +980,11 @@ void rk_kzg_ctx_destroy(rk_kzg_ctx* ctx) {
 int rk_kzg_ctx_window_bits(const rk_kzg_ctx* ctx) { return ctx ? ctx->geom.c : 0; }
 int rk_kzg_ctx_num_devices(const rk_kzg_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 uint64_t rk_kzg_ctx_table_bytes(const rk_kzg_ctx* ctx) { return ctx ? ctx->devs[0]->table_bytes : 0; }
+int rk_kzg_ctx_window_reduced(const rk_kzg_ctx* ctx) {
+    if (!ctx) return 0;
+    for (auto* d : ctx->devs) if (d->window_reduced) return 1;
+    return 0;
+}
 
 rk_status rk_kzg_ctx_export_settings(rk_kzg_ctx* ctx, int kind, uint8_t* out, size_t* len) {
     if (!ctx || !out || !len) return fail(RK_ERR_ARG, "null argument");
@@ -866,11 +992,13 @@ rk_status rk_kzg_ctx_export_settings(rk_kzg_ctx* ctx, int kind, uint8_t* out, si
     if (!need) return fail(RK_ERR_ARG, "kind must be 0 (raw) or 1 (bincode)");
     if (*len < need) { *len = need; return fail(RK_ERR_BAD_LENGTH, "output buffer too small, need %zu", need); }
     DeviceCtx* d = ctx->devs[0];
+    DeviceGuard dg;
     std::lock_guard<std::mutex> lock(d->mu);
     CUDA_TRY(cudaSetDevice(d->dev));
+    DevBuf buf;
     uint8_t* d_buf = nullptr;
     const size_t g1b = 144ull * NPTS, g2b = 288ull * N_G2, rb = 32ull * 4097;
-    CUDA_TRY(cudaMalloc(&d_buf, g1b + g2b + 3 * rb + 192 * N_G2));
+    CUDA_TRY(buf.alloc(&d_buf, g1b + g2b + 3 * rb + 192 * N_G2));
     uint8_t *d_g1 = d_buf, *d_g2 = d_buf + g1b, *d_r0 = d_g2 + g2b, *d_r1 = d_r0 + rb, *d_r2 = d_r1 + rb, *d_g2in = d_r2 + rb;
     launch_k_setup_to_ref(NPTS / 64, 64, 0, 0, d->g1_aff, NPTS, d_g1);
     // G2: x.c0 x.c1 y.c0 y.c1 (BE) -> 6 Montgomery coordinates with Z = (1, 0)
@@ -880,7 +1008,7 @@ rk_status rk_kzg_ctx_export_settings(rk_kzg_ctx* ctx, int kind, uint8_t* out, si
         g2six[288 * i + 4 * 48 + 47] = 1;
     }
     uint8_t* d_g2be = nullptr;
-    CUDA_TRY(cudaMalloc(&d_g2be, g2six.size()));
+    CUDA_TRY(buf.alloc(&d_g2be, g2six.size()));
     CUDA_TRY(cudaMemcpy(d_g2be, g2six.data(), g2six.size(), cudaMemcpyHostToDevice));
     launch_k_fp_be_to_ref((6 * N_G2 + 63) / 64, 64, 0, 0, d_g2be, 6 * N_G2, d_g2);
     launch_k_roots_export((4097 + 63) / 64, 64, 0, 0, 0, 4097, d_r0);
@@ -890,7 +1018,6 @@ rk_status rk_kzg_ctx_export_settings(rk_kzg_ctx* ctx, int kind, uint8_t* out, si
     CUDA_TRY(cudaGetLastError());
     std::vector<uint8_t> h(g1b + g2b + 3 * rb);
     CUDA_TRY(cudaMemcpy(h.data(), d_buf, h.size(), cudaMemcpyDeviceToHost));
-    cudaFree(d_buf); cudaFree(d_g2be);
     const uint8_t *h_g1 = h.data(), *h_g2 = h.data() + g1b, *h_r0 = h_g2 + g2b, *h_r1 = h_r0 + rb, *h_r2 = h_r1 + rb;
     memset(out, 0, need);
     auto put_le64 = [&](size_t off, uint64_t v) { memcpy(out + off, &v, 8); };
@@ -950,6 +1077,17 @@ rk_status rk_compute_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, cons
     return run_batch(ctx, a);
 }
 
+rk_status rk_compute_blob_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments, size_t n,
+                                          uint8_t* out_proofs, uint8_t* per_blob_status) {
+    if (!out_proofs || !commitments) return fail(RK_ERR_ARG, "commitments and out_proofs are required");
+    if (ctx && is_device_ptr(commitments) && ctx->devs.size() != 1) return fail(RK_ERR_ARG, "device pointers need a single-device context");
+    if (ctx) { rk_status pst = check_ptr_device(ctx, commitments, "commitments"); if (pst != RK_OK) return pst; }
+    BatchArgs a{};
+    a.mode = MODE_BLOB_PROOF; a.blobs = blobs; a.cins = commitments; a.n = n;
+    a.out_proof = out_proofs; a.status = per_blob_status;
+    return run_batch(ctx, a);
+}
+
 // Execute a group of same-mode single-blob requests as one batch and fill in their results.
 static void exec_requests(rk_kzg_ctx* ctx, const std::vector<SingleReq*>& batch) {
     const size_t k = batch.size();
@@ -985,6 +1123,7 @@ static void exec_requests(rk_kzg_ctx* ctx, const std::vector<SingleReq*>& batch)
 // same mode are waiting.  Blocks until r is done.
 static rk_status submit_single(rk_kzg_ctx* ctx, SingleReq& r) {
     constexpr size_t MAX_MERGE = 64;
+    DeviceGuard dg;
     cudaSetDevice(ctx->devs[0]->dev);
     if (is_device_ptr(r.blob)) {                       // device-resident blob: nothing to stage, run alone
         exec_requests(ctx, {&r});
@@ -1096,6 +1235,7 @@ rk_status rk_verify_kzg_proof(rk_kzg_ctx* ctx, const uint8_t commitment[48], con
     if (!ctx || !commitment || !z || !y || !proof || !out_ok) return fail(RK_ERR_ARG, "null argument");
     *out_ok = 0;
     DeviceCtx* d = ctx->devs[0];
+    DeviceGuard dg;
     std::lock_guard<std::mutex> lock(d->mu);
     CUDA_TRY(cudaSetDevice(d->dev));
     DevBuf buf;
@@ -1114,6 +1254,11 @@ rk_status rk_verify_kzg_proof_batch(rk_kzg_ctx* ctx, const uint8_t* commitments,
     if (n == 0) { *out_ok = 1; return RK_OK; }
     if (!commitments || !zs || !ys || !proofs) return fail(RK_ERR_ARG, "null argument");
     DeviceCtx* d = ctx->devs[0];
+    DeviceGuard dg;
+    for (const void* p : {(const void*)commitments, (const void*)zs, (const void*)ys, (const void*)proofs}) {
+        rk_status pst = check_ptr_device(ctx, p, "an input array");
+        if (pst != RK_OK) return pst;
+    }
     std::lock_guard<std::mutex> lock(d->mu);
     CUDA_TRY(cudaSetDevice(d->dev));
     // one random-linear-combination transcript (and one two-pairing check) per <= 16384 tuples
@@ -1162,6 +1307,11 @@ rk_status rk_decode_blob_data_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_
     if (n == 0) return RK_OK;
     if (!blobs) return fail(RK_ERR_ARG, "null blobs pointer");
     DeviceCtx* d = ctx->devs[0];
+    DeviceGuard dg;
+    for (const void* p : {(const void*)blobs, (const void*)out, (const void*)out_len}) {
+        rk_status pst = check_ptr_device(ctx, p, "a buffer");
+        if (pst != RK_OK) return pst;
+    }
     std::lock_guard<std::mutex> lock(d->mu);
     CUDA_TRY(cudaSetDevice(d->dev));
     const bool blobs_dev = is_device_ptr(blobs), out_dev = is_device_ptr(out);
@@ -1179,7 +1329,6 @@ rk_status rk_decode_blob_data_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_
         if (blobs_dev) {
             d_blobs = blobs + first * BLOB_BYTES;
         } else {
-            if (!s.d_blobs) CUDA_TRY(cudaMalloc(&s.d_blobs, chunk * BLOB_BYTES));
             CUDA_TRY(cudaMemcpyAsync(s.d_blobs, blobs + first * BLOB_BYTES, (size_t)cnt * BLOB_BYTES, cudaMemcpyHostToDevice, st));
             d->stats.h2d_bytes += (uint64_t)cnt * BLOB_BYTES;
             d_blobs = s.d_blobs;
@@ -1195,6 +1344,30 @@ rk_status rk_decode_blob_data_batch(rk_kzg_ctx* ctx, const uint8_t* blobs, size_
             d->stats.d2h_bytes += (uint64_t)cnt * (BLOBDATA_STRIDE + 4);
         }
         CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return RK_OK;
+}
+
+rk_status rk_synth_blobs(rk_kzg_ctx* ctx, uint64_t seed, uint32_t first_blob, size_t n, uint8_t* out) {
+    if (!ctx || !out) return fail(RK_ERR_ARG, "null argument");
+    if (n == 0) return RK_OK;
+    if (n > 0xffffffffull - first_blob) return fail(RK_ERR_ARG, "blob index exceeds 32 bits");
+    DeviceCtx* d = ctx->devs[0];
+    DeviceGuard dg;
+    rk_status pst = check_ptr_device(ctx, out, "out");
+    if (pst != RK_OK) return pst;
+    std::lock_guard<std::mutex> lock(d->mu);
+    CUDA_TRY(cudaSetDevice(d->dev));
+    const bool out_dev = is_device_ptr(out);
+    const size_t chunk = (size_t)d->chunk;
+    for (size_t first = 0; first < n; first += chunk) {
+        const size_t cnt = std::min(chunk, n - first);
+        uint8_t* dst = out_dev ? out + first * BLOB_BYTES : d->slot[0].d_q;
+        launch_k_synth_blobs((unsigned)(cnt * NPTS / 256), 256, 0, d->s_main, seed, first_blob + (uint32_t)first, (uint32_t)cnt, dst);
+        d->stats.total_launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (!out_dev) CUDA_TRY(cudaMemcpyAsync(out + first * BLOB_BYTES, dst, cnt * BLOB_BYTES, cudaMemcpyDeviceToHost, d->s_main));
+        CUDA_TRY(cudaStreamSynchronize(d->s_main));
     }
     return RK_OK;
 }
@@ -1223,8 +1396,7 @@ rk_status rk_measure_imad_peak(int device, double* out_macs_per_sec, double* out
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
         return fail(RK_ERR_CUDA, "no such CUDA device %d", device);
-    int prev = 0;
-    cudaGetDevice(&prev);
+    DeviceGuard dg;
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -1251,7 +1423,6 @@ rk_status rk_measure_imad_peak(int device, double* out_macs_per_sec, double* out
         cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
         *out_sm_clock_mhz = khz / 1000.0;
     }
-    cudaSetDevice(prev);
     return RK_OK;
 }
 

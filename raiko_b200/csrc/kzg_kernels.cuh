@@ -526,7 +526,7 @@ __global__ void __maxnreg__(248) k_msm(MsmParams prm) { msm_body<256, 1, 1, fals
 
 // ---------------------------------------------------------------------------
 // k_finalize: one thread per blob.  Sums the blob's partial sums, converts to affine
-// (one Fermat inversion), writes the 48-byte compressed point, and optionally the
+// (one division-step inversion, fe_inv_safegcd), writes the 48-byte compressed point, and optionally the
 // versioned hash  sha256(commitment) with byte 0 = 0x01  (eip4844.rs:91-95).
 // A blob flagged `bad` (non-canonical field element; Eip4844Error::DeserializeBlob)
 // gets zeroed outputs and status RK_ERR_NONCANONICAL_FE (= 2).
@@ -1178,6 +1178,47 @@ __global__ void __launch_bounds__(128) k_table_normalize(TableGeom g, uint32_t d
 
 #endif  // RK_TU_TABLE
 // ---------------------------------------------------------------------------
+// Synthetic blobs of the measurement contract, generated where they are used:
+//   fe(b, i) = BE_int(sha256("raiko-kzg-bench-v1" | LE64(seed) | LE32(b) | LE32(i))) mod r,
+// written as 32 big-endian bytes -- the same rule tests/kzg_testlib.py::synthetic_blob and the
+// golden vectors C5 / C6 (seed 20241018) use on the host, so device-resident bench input is
+// byte-identical to what the oracle hashes.  One thread per field element, one compression.
+// ---------------------------------------------------------------------------
+#ifdef RK_TU_PATH
+__global__ void __launch_bounds__(256) k_synth_blobs(uint64_t seed, uint32_t first_blob, uint32_t nblobs, uint8_t* out) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (uint64_t)nblobs * NPTS) return;
+    const uint32_t b = first_blob + (uint32_t)(gid >> 12), i = (uint32_t)gid & (NPTS - 1);
+    uint8_t m[64];
+    const char tag[19] = "raiko-kzg-bench-v1";
+#pragma unroll
+    for (int k = 0; k < 64; k++) m[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 18; k++) m[k] = (uint8_t)tag[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) m[18 + k] = (uint8_t)(seed >> (8 * k));
+#pragma unroll
+    for (int k = 0; k < 4; k++) { m[26 + k] = (uint8_t)(b >> (8 * k)); m[30 + k] = (uint8_t)(i >> (8 * k)); }
+    m[34] = 0x80;
+    m[62] = (uint8_t)((34 * 8) >> 8); m[63] = (uint8_t)(34 * 8);
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k] = load_be32(m + 4 * k);
+    Sha256State st;
+    sha256_init(st);
+    sha256_compress(st, w);
+    uint32_t sw[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sw[k] = st.h[7 - k];
+    Fr c;
+    fe_unpack<FrTag>(c, sw);
+    fe_cond_sub_mod<FrTag>(c);                     // digest < 2^256 < 3r: two conditional subtractions
+    fe_cond_sub_mod<FrTag>(c);
+    fr_store_be(out + 32 * gid, c);
+}
+#endif  // RK_TU_PATH
+
+// ---------------------------------------------------------------------------
 // Integer-multiply peak (roofline denominator): independent mad.wide.u32 chains.
 // ---------------------------------------------------------------------------
 #ifdef RK_TU_PATH
@@ -1383,7 +1424,7 @@ __global__ void __launch_bounds__(VR_THREADS) k_verify_reduce(const G1Xyzz* a, c
     }
     Fr ts;
     fe_zero(ts);
-    for (int i = tid; i < n; i += VR_THREADS) fe_add(ts, ts, t[i]);       // n * 1.1 r must stay < 2^270: n < 30 000 per call
+    for (int i = tid; i < n; i += VR_THREADS) fe_add(ts, ts, t[i]);       // n * 1.1 r must stay < 2^270 (n < 30 000); the host caps a call at VERIFY_MAX_N = 16384
     sht[tid] = ts;
     __syncthreads();
     if (tid == 0) {

@@ -21,6 +21,7 @@ namespace rk {
     X(k_sha_blob_duo, (const uint8_t* blobs, int nblobs, uint8_t* out_hash, int stride), (blobs, nblobs, out_hash, stride)) \
     X(k_fr_eval_quot, (FrParams p), (p))                                                       \
     X(k_imad_peak, (uint64_t* out, uint32_t seed, int iters), (out, seed, iters))               \
+    X(k_synth_blobs, (uint64_t seed, uint32_t first_blob, uint32_t nblobs, uint8_t* out), (seed, first_blob, nblobs, out)) \
     X(k_decode_blob_data, (const uint8_t* blobs, int nblobs, uint8_t* out, uint32_t* out_len), (blobs, nblobs, out, out_len))
 
 #define RK_KERNELS_TABLE(X)                                                                    \

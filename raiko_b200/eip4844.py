@@ -20,7 +20,7 @@ __all__ = [
     "ComputeKzgProof", "KzgSettings", "KZGSettings", "kzg_settings", "set_kzg_settings", "get_evaluation_point",
     "proof_of_equivalence", "calc_kzg_proof", "calc_kzg_proof_with_point", "calc_kzg_proof_commitment",
     "commitment_to_version_hash", "kzg_proof_to_bytes", "blob_to_kzg_commitment", "compute_kzg_proof",
-    "kzg_to_versioned_hash", "verify_kzg_proof", "verify_kzg_proof_batch", "verify_blob_kzg_proof_batch", "commit_batch", "commit_prove_batch", "compute_kzg_proof_batch", "BatchResult",
+    "kzg_to_versioned_hash", "verify_kzg_proof", "verify_kzg_proof_batch", "verify_blob_kzg_proof_batch", "commit_batch", "commit_prove_batch", "compute_kzg_proof_batch", "compute_blob_kzg_proof_batch", "BatchResult",
     "DEFAULT_SETTINGS_PATH",
 ]
 
@@ -128,6 +128,20 @@ class KzgSettings:
     @property
     def table_bytes(self) -> int:
         return int(self._lib.rk_kzg_ctx_table_bytes(self._ctx))
+
+    @property
+    def window_reduced(self) -> bool:
+        """True when the library had to pick a window narrower than 15 bits for lack of free HBM."""
+        return bool(self._lib.rk_kzg_ctx_window_reduced(self._ctx))
+
+    def synth_blobs(self, out, first_blob: int = 0, seed: int = 20241018):
+        """Fill `out` (a uint8 torch tensor / numpy array of n * 131072 bytes, host or CUDA) with the
+        SURVEY.md 8(d) synthetic blobs first_blob .. first_blob + n - 1 (bench / test tooling)."""
+        b = _Buf(out)
+        if b.nbytes % BYTES_PER_BLOB:
+            raise ValueError("output must be a whole number of blobs")
+        _check(self._lib.rk_synth_blobs(self._ctx, int(seed), int(first_blob), b.nbytes // BYTES_PER_BLOB, b.ptr))
+        return out
 
     def export(self, kind: str = "bincode") -> bytes:
         """Re-serialise in the reference's layouts (host/src/bin/gen_kzg_settings.rs:8-22)."""
@@ -359,6 +373,20 @@ def commit_prove_batch(blobs, settings: Optional[KzgSettings] = None) -> BatchRe
     _check(s._lib.rk_commit_prove_batch(s._ctx, buf.ptr, n, c, vh, x, y, pr, st))
     return BatchResult(n, _split(c.raw, 48), _split(vh.raw, 32), _split(x.raw, 32), _split(y.raw, 32),
                        _split(pr.raw, 48), list(st.raw))
+
+
+def compute_blob_kzg_proof_batch(blobs, commitments: Sequence[bytes], settings: Optional[KzgSettings] = None) -> BatchResult:
+    """compute_blob_kzg_proof (Deneb spec) per blob: EIP-4844 challenge from (blob, commitment), then
+    the proof there -- the proofs verify_blob_kzg_proof_batch accepts."""
+    s = _s(settings)
+    buf, n = _blobs_buf(blobs)
+    craw = b"".join(bytes(c) for c in commitments)
+    if len(craw) != 48 * n:
+        raise ValueError("need one 48-byte commitment per blob")
+    pr = ctypes.create_string_buffer(48 * n)
+    st = ctypes.create_string_buffer(n)
+    _check(s._lib.rk_compute_blob_kzg_proof_batch(s._ctx, buf.ptr, _cptr(craw), n, pr, st))
+    return BatchResult(n, commitments=_split(craw, 48), proofs=_split(pr.raw, 48), status=list(st.raw))
 
 
 def compute_kzg_proof_batch(blobs, zs: Sequence[bytes], settings: Optional[KzgSettings] = None) -> BatchResult:

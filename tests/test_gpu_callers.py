@@ -89,3 +89,26 @@ def test_blob_data_codec(gpu_settings, pyoracle):
     assert got == [o.decode_blob_data(b) for b in allb]
     assert got[:len(datas)] == datas and all(g == b"" for g in got[len(datas):len(datas) + 5])
     assert callers.decode_blob_data(blobs[10], gpu_settings) == datas[10]
+
+
+def test_reference_blob_fixture(gpu_settings):
+    """The only real blob the reference ships (core/src/preflight.rs:480-525): GPU codec, GPU
+    commitment / challenge / evaluation / proof against the committed fixture
+    (tests/golden/reference_blob_preflight.json, made by tests/golden/make_reference_blob.py)."""
+    import hashlib
+    import raiko_b200 as rk
+    from raiko_b200 import callers
+    from test_callers_host import reference_blob
+    fx, blob = reference_blob()
+    dec = callers.decode_blob_data(blob, gpu_settings)
+    assert len(dec) == 1200 and hashlib.sha256(dec).hexdigest() == fx["decoded_sha256"] and dec[:3].hex() == "f904ad"
+    txs = callers.decode_transactions(dec)
+    assert len(txs) == 3 and all(t[0] == 2 for t in txs)
+    res = rk.commit_prove_batch([blob], gpu_settings)
+    assert res.status == [0]
+    assert (res.commitments[0].hex(), res.versioned_hashes[0].hex(), res.xs[0].hex(), res.ys[0].hex(), res.proofs[0].hex()) == \
+        (fx["commitment"], fx["versioned_hash"], fx["x"], fx["y"], fx["proof"])
+    assert rk.verify_kzg_proof(res.commitments[0], res.xs[0], res.ys[0], res.proofs[0], gpu_settings)
+    # the blob is not zlib data: get_tx_list's unwrap_or_default gives an empty tx list, like the reference
+    assert callers.get_tx_list(True, "taiko_a7", True, blob, gpu_settings) == b""
+    assert callers.generate_transactions(True, "taiko_a7", True, blob, anchor_tx=b"\xc1\x01", settings=gpu_settings) == [b"\xc1\x01"]

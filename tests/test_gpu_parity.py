@@ -233,19 +233,119 @@ def test_thread_safety(gpu_settings, golden):
 
 
 def test_multi_gpu_sharding(golden, ref):
+    """One context over every GPU of the box (the library's own sharding: contiguous shards, one host
+    thread per device, host-side gather), host pointers, a batch size no device count divides, and
+    more than one chunk per device."""
+    code = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests")); sys.path.insert(0, os.path.join(%r, "oracle"))
+import torch
+import raiko_b200 as rk
+import kzg_ref
+from kzg_testlib import SETUP, synthetic_blob
+ndev = torch.cuda.device_count()
+s = rk.KzgSettings(devices=list(range(ndev)), window_bits=8)
+assert s.num_devices == ndev
+ref = kzg_ref.RefSettings(open(SETUP, "rb").read())
+n = 8 * ndev + 5                                       # not divisible by 2, 4 or 8
+blobs = [synthetic_blob(b, seed=4242) for b in range(n)]
+bad = bytearray(blobs[n // 2]); bad[32 * 100:32 * 101] = b"\xff" * 32; blobs[n // 2] = bytes(bad)   # one non-canonical blob mid-batch
+before = torch.cuda.current_device()
+res = rk.commit_prove_batch(blobs, s)
+assert torch.cuda.current_device() == before           # the library restores the caller's device
+one = rk.KzgSettings(devices=[0], window_bits=8)
+res1 = rk.commit_prove_batch(blobs, one)
+for f in ("commitments", "versioned_hashes", "xs", "ys", "proofs", "status"):
+    assert getattr(res, f) == getattr(res1, f), f
+assert res.status[n // 2] == 2 and sum(res.status) == 2
+for i in sorted({0, 1, n // 3, n - 1} | {n * g // ndev for g in range(ndev)} | {n * g // ndev - 1 for g in range(1, ndev)}):
+    if i == n // 2: continue
+    assert (res.commitments[i], res.versioned_hashes[i], res.xs[i], res.ys[i], res.proofs[i]) == ref.commit_prove(blobs[i]), i
+# a device pointer on another GPU than the context's first device is refused, not dereferenced
+if ndev >= 2:
+    from raiko_b200 import _native
+    lib = _native.load()
+    t = torch.zeros(131072, dtype=torch.uint8, device="cuda:1")
+    o = torch.zeros(48, dtype=torch.uint8, device="cuda:1")
+    st = lib.rk_commit_batch(one._ctx, t.data_ptr(), 1, o.data_ptr(), None, None)
+    assert st == _native.RK_ERR_ARG and "GPU 1" in _native.last_error(), (st, _native.last_error())
+print("MULTI_OK ndev=%%d n=%%d launches=%%d" %% (ndev, n, s.stats()["total_launches"]))
+''' % (ROOT, ROOT, ROOT)
     import torch
-    import raiko_b200 as rk
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    s = rk.KzgSettings(devices=list(range(min(4, torch.cuda.device_count()))), window_bits=8)
-    blobs = [synthetic_blob(b, seed=4242) for b in range(11)]
-    res = rk.commit_prove_batch(blobs, s)
-    for i in (0, 3, 5, 10):
-        assert (res.commitments[i], res.versioned_hashes[i], res.xs[i], res.ys[i], res.proofs[i]) == ref.commit_prove(blobs[i])
-    one = rk.KzgSettings(devices=[0], window_bits=8)
-    res1 = rk.commit_prove_batch(blobs, one)
-    assert res1.commitments == res.commitments and res1.proofs == res.proofs and res1.ys == res.ys
-    s.close(); one.close()
+    env = dict(os.environ, RAIKO_KZG_CHUNK="3")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "MULTI_OK" in out.stdout, out.stdout + out.stderr
+    print(out.stdout.strip().splitlines()[-1])
+
+
+def test_device_guard_and_window_report(gpu_settings):
+    """Entry points leave the caller's current device alone (ADVICE r1) and report an auto-narrowed window."""
+    import torch
+    import raiko_b200 as rk
+    before = torch.cuda.current_device()
+    rk.commit_batch([bytes(131072)], gpu_settings)
+    assert torch.cuda.current_device() == before
+    assert gpu_settings.window_reduced is False        # window_bits was passed explicitly
+
+
+def test_synthetic_blobs_on_device_equal_the_host_generator(gpu_settings):
+    """rk_synth_blobs (bench input, SURVEY.md 8(d)) is byte-identical to tests/kzg_testlib.synthetic_blob,
+    i.e. to the recipe of golden vectors C5 / C6; device and host outputs, first_blob offset."""
+    import torch
+    t = torch.zeros((5, 131072), dtype=torch.uint8, device="cuda")
+    gpu_settings.synth_blobs(t, first_blob=0)
+    h = t.cpu().numpy()
+    for b in (0, 1, 4):
+        assert h[b].tobytes() == synthetic_blob(b), b
+    import numpy as np
+    host = np.zeros((3, 131072), dtype=np.uint8)
+    gpu_settings.synth_blobs(host, first_blob=70000, seed=7)
+    assert host[2].tobytes() == synthetic_blob(70002, seed=7)
+
+
+def test_wave_aware_tail_split(ref):
+    """A chunk of more than one wave of one-warp-per-blob MSM work is launched as its whole waves
+    plus a separately planned remainder (two MSM launches, two finalize launches): same bytes as the
+    single-launch schedule (RAIKO_KZG_WAVE_TAIL=0), and spot-checked against the oracle."""
+    code = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests")); sys.path.insert(0, os.path.join(%r, "oracle"))
+import torch
+import raiko_b200 as rk
+from raiko_b200 import _native
+lib = _native.load()
+sm = torch.cuda.get_device_properties(0).multi_processor_count
+n = sm * 16 + 301                                       # one wave of the affine kernel + a remainder
+s = rk.KzgSettings(window_bits=8)
+blobs = torch.zeros((n, 131072), dtype=torch.uint8, device="cuda")
+s.synth_blobs(blobs, first_blob=1000, seed=5)
+oc = torch.zeros((n, 48), dtype=torch.uint8, device="cuda"); ovh = torch.zeros((n, 32), dtype=torch.uint8, device="cuda"); ost = torch.zeros(n, dtype=torch.uint8, device="cuda")
+s.stats_reset()
+assert lib.rk_commit_batch(s._ctx, blobs.data_ptr(), n, oc.data_ptr(), ovh.data_ptr(), ost.data_ptr()) == 0, _native.last_error()
+torch.cuda.synchronize()
+print("WAVE", os.environ.get("RAIKO_KZG_WAVE_TAIL", "1"), s.stats()["msm_launches"], oc.cpu().numpy().tobytes().hex()[:0])
+import hashlib
+print("DIGEST", hashlib.sha256(oc.cpu().numpy().tobytes() + ovh.cpu().numpy().tobytes() + ost.cpu().numpy().tobytes()).hexdigest())
+for i in (0, sm * 16 - 1, sm * 16, n - 1):
+    print("ROW", i, blobs[i].cpu().numpy().tobytes().hex()[:0], oc[i].cpu().numpy().tobytes().hex())
+''' % (ROOT, ROOT, ROOT)
+    outs = {}
+    for tail in ("1", "0"):
+        env = dict(os.environ, RAIKO_KZG_WAVE_TAIL=tail)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[tail] = r.stdout
+    launches = {t: int([l for l in outs[t].splitlines() if l.startswith("WAVE")][0].split()[2]) for t in outs}
+    assert launches == {"1": 2, "0": 1}, launches
+    dig = {t: [l for l in outs[t].splitlines() if l.startswith("DIGEST")][0] for t in outs}
+    assert dig["1"] == dig["0"]
+    import torch
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    for line in [l for l in outs["1"].splitlines() if l.startswith("ROW")]:
+        _, i, c = line.split()
+        assert ref.commit(synthetic_blob(1000 + int(i), seed=5)).hex() == c, i
 
 
 def test_imad_peak_microbenchmark():

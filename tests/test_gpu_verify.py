@@ -51,6 +51,23 @@ def _eip4844_challenges(pyoracle, blobs, commitments):
     return [o.fr_to_bytes(o.compute_challenge(b, c)) for b, c in zip(blobs, commitments)]
 
 
+def test_compute_blob_kzg_proof_batch_equals_the_oracle(gpu_settings, pyoracle):
+    """rk_compute_blob_kzg_proof_batch (Deneb compute_blob_kzg_proof: EIP-4844 challenge, then the
+    proof) against the Python oracle, byte for byte, and through verify_blob_kzg_proof_batch."""
+    import raiko_b200 as rk
+    o, s = pyoracle
+    blobs = [synthetic_blob(b, seed=31337) for b in range(3)] + [blob_from_recipe({"kind": "mod64"}), bytes(131072)]
+    commitments = rk.commit_batch(blobs, gpu_settings).commitments
+    res = rk.compute_blob_kzg_proof_batch(blobs, commitments, gpu_settings)
+    assert res.status == [0] * len(blobs)
+    for i in (0, 3, 4):
+        assert res.proofs[i] == o.compute_blob_kzg_proof(blobs[i], commitments[i], s), i
+    assert rk.verify_blob_kzg_proof_batch(blobs, commitments, res.proofs, gpu_settings)
+    bad = bytearray(blobs[1]); bad[0:32] = b"\xff" * 32
+    res2 = rk.compute_blob_kzg_proof_batch([bytes(bad)], commitments[1:2], gpu_settings)
+    assert res2.status == [2] and res2.proofs[0] == bytes(48)
+
+
 def test_verify_blob_kzg_proof_batch(gpu_settings, pyoracle):
     import raiko_b200 as rk
     o, s = pyoracle
