@@ -143,6 +143,8 @@ struct DeviceCtx {
     bool wave_tail = true;                     // wave-aware chunk schedule and tail split (RAIKO_KZG_WAVE_TAIL=0: off)
     uint32_t* aff_scratch = nullptr;       // sm_count x chains x 39 words x 256 threads
     uint32_t recode_h[8] = {0};
+    // RAIKO_KZG_TRACE=1: per-chunk timeline of every batch call (H2D, compute, D2H) on stderr
+    bool trace = false;
     // stats
     bool stats_on = false;
     std::vector<KernelTimer> timers;
@@ -344,6 +346,7 @@ rk_status alloc_slots(DeviceCtx* d) {
     if (const char* e = getenv("RAIKO_KZG_AFFINE_MIN_ENTRIES")) d->aff_min_entries = std::max(1, atoi(e));
     if (const char* e = getenv("RAIKO_KZG_MAX_SPLITS_LOG2")) d->max_splits_log2 = std::min(7, std::max(0, atoi(e)));
     if (const char* e = getenv("RAIKO_KZG_WAVE_TAIL")) d->wave_tail = atoi(e) != 0;
+    if (const char* e = getenv("RAIKO_KZG_TRACE")) d->trace = atoi(e) != 0;
     if (d->msm_affine) {
         CUDA_TRY(configure_k_msm_affine());
         CUDA_TRY(cudaMalloc(&d->aff_scratch, (size_t)d->sm_count * d->aff_chains * AFF_WORDS * (32 * d->aff_warps) * sizeof(uint32_t)));
@@ -605,12 +608,23 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
     };
 
     const std::vector<size_t> sizes = chunk_schedule(d, a.n, !a.blobs_on_device);
+    // optional timeline: five timed events per chunk (H2D begin / end, compute begin / end, D2H end)
+    struct ChunkTrace { cudaEvent_t e[5]; int cnt; int nseg; };
+    std::vector<ChunkTrace> tr;
+    cudaEvent_t tr0 = nullptr;
+    if (d->trace) {
+        tr.resize(sizes.size());
+        for (auto& t : tr) for (auto& e : t.e) cudaEventCreate(&e);
+        cudaEventCreate(&tr0);
+        cudaEventRecord(tr0, d->s_in);
+    }
     size_t first = 0;
     for (size_t ci = 0; ci < sizes.size(); ci++) {
         ChunkSlot& s = d->slot[ci & 1];
         rk_status st = drain(s);
         if (st != RK_OK) return st;
         const int cnt = (int)sizes[ci];
+        if (d->trace) { tr[ci].cnt = cnt; cudaEventRecord(tr[ci].e[0], d->s_in); }
 
         // ---- input ---------------------------------------------------------------------
         const uint8_t* d_blobs;
@@ -637,8 +651,10 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             CUDA_TRY(cudaMemcpy2DAsync(o + OFF_VH, OUT_STRIDE, a.vhs + 32 * first, 32, 32, (size_t)cnt,
                                        cudaMemcpyHostToDevice, d->s_in));
         }
+        if (d->trace) cudaEventRecord(tr[ci].e[1], d->s_in);
         CUDA_TRY(cudaEventRecord(s.ev_in, d->s_in));
         CUDA_TRY(cudaStreamWaitEvent(d->s_main, s.ev_in, 0));
+        if (d->trace) cudaEventRecord(tr[ci].e[2], d->s_main);
         CUDA_TRY(cudaMemsetAsync(s.d_bad, 0, sizeof(uint32_t) * cnt, d->s_main));
         CUDA_TRY(cudaMemsetAsync(o_stat, 0, (size_t)cnt, d->s_main));
 
@@ -683,6 +699,7 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             d->stats.total_launches++;
         }
         CUDA_TRY(cudaGetLastError());
+        if (d->trace) cudaEventRecord(tr[ci].e[3], d->s_main);
         CUDA_TRY(cudaEventRecord(s.ev_done, d->s_main));
         // ---- output ----------------------------------------------------------------------
         CUDA_TRY(cudaStreamWaitEvent(d->s_out, s.ev_done, 0));
@@ -703,6 +720,7 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
             CUDA_TRY(cudaMemcpyAsync(s.h_out + chunk * OUT_STRIDE, o_stat, (size_t)cnt, cudaMemcpyDeviceToHost, d->s_out));
             d->stats.d2h_bytes += (uint64_t)cnt * (OUT_STRIDE + 1);
         }
+        if (d->trace) cudaEventRecord(tr[ci].e[4], d->s_out);
         CUDA_TRY(cudaEventRecord(s.ev_out, d->s_out));
         // only now does the slot hold results that drain() may copy out
         s.first = first; s.count = (size_t)cnt; s.busy = true;
@@ -716,6 +734,23 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
     CUDA_TRY(cudaStreamSynchronize(d->s_sha));
     CUDA_TRY(cudaStreamSynchronize(d->s_out));
     timers_collect(d);
+    if (d->trace) {
+        CUDA_TRY(cudaStreamSynchronize(d->s_in));
+        std::string line;
+        char buf[256];
+        snprintf(buf, sizeof buf, "[raiko_kzg trace] GPU %d mode %d n %zu %s input, %zu chunks; ms from the first H2D enqueue: blobs | h2d begin..end | compute begin..end | d2h end\n",
+                 d->dev, (int)a.mode, a.n, a.blobs_on_device ? "device" : "host", sizes.size());
+        line += buf;
+        for (size_t ci = 0; ci < tr.size(); ci++) {
+            float t[5];
+            for (int k = 0; k < 5; k++) { t[k] = 0.f; cudaEventElapsedTime(&t[k], tr0, tr[ci].e[k]); }
+            snprintf(buf, sizeof buf, "[raiko_kzg trace]   chunk %2zu  %5d | %8.2f .. %8.2f | %8.2f .. %8.2f | %8.2f\n", ci, tr[ci].cnt, t[0], t[1], t[2], t[3], t[4]);
+            line += buf;
+        }
+        fputs(line.c_str(), stderr);
+        for (auto& t : tr) for (auto& e : t.e) cudaEventDestroy(e);
+        cudaEventDestroy(tr0);
+    }
     reset.ok = true;
     return RK_OK;
 }

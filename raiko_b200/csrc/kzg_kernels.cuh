@@ -771,19 +771,42 @@ constexpr int FR_THREADS = 256;
 constexpr int FR_PER_THREAD = NPTS / FR_THREADS;   // 16
 
 #ifdef RK_TU_PATH
+__device__ __forceinline__ void shfl_fr(Fr& r, const Fr& a, int src_lane) {
+#pragma unroll
+    for (int i = 0; i < FR_N; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src_lane);
+}
+// Sum of `v` over the 256 threads of the CTA, returned to thread 0 (other threads: garbage).
+// Warp shuffle tree, then the 8 warp sums through shared memory (ws[8]); limb-wise adds with a
+// carry pass, so the bound on the result is the bound on the plain sum.
+__device__ __forceinline__ void cta_sum_fr(Fr& v, Fr* ws, int tid) {
+    const int lane = tid & 31;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < FR_N; i++) o.v[i] = __shfl_down_sync(0xffffffffu, v.v[i], d);
+        fe_add(v, v, o);
+    }
+    if (lane == 0) ws[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < FR_THREADS / 32; w++) fe_add(v, v, ws[w]);
+    }
+}
+
 __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // per-element prefix products / inverses live in global scratch (coalesced: thread t touches
     // element k*256 + t), not in shared memory: 147 KB per blob would pin one CTA per SM and leave
-    // the SM idle during the CTA's serial inversion.
+    // the SM idle during the CTA's serial sections.
     Fr* inv_s = prm.inv_scratch + (size_t)blockIdx.x * NPTS;
-    Fr* tot_s = reinterpret_cast<Fr*>(smem_raw);             // [256] per-thread totals -> inverses
-    Fr* lane_s = tot_s + FR_THREADS;                         // [32]
-    Fr* bc_s = lane_s + 32;                                  // [4] broadcast: z, y, scale, zinv
+    Fr* wtot_s = reinterpret_cast<Fr*>(smem_raw);            // [8] warp totals -> per-warp cofactors
+    Fr* wsum_s = wtot_s + 8;                                 // [8] warp partial sums of the reductions
+    Fr* bc_s = wsum_s + 8;                                   // [4] broadcast: z, y, canonical y, (z^4096 - 1) / 4096
     __shared__ int s_m;                                      // index with w_m == z, or -1
     __shared__ int s_bad;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int blob = blockIdx.x;
     const uint8_t* bp = prm.blobs + (size_t)blob * BLOB_BYTES;
 
@@ -815,62 +838,86 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
     Fr run;
     fe_const<FrTag, FR_ONE>(run);
     for (int k = 0; k < FR_PER_THREAD; k++) {
-        const int i = k * FR_THREADS + tid;   // interleaved: coalesced loads, conflict-free smem
+        const int i = k * FR_THREADS + tid;   // interleaved: coalesced loads
         Fr w = prm.roots_brp[i], d;
         fe_sub<FrTag, 2>(d, z, w);                 // < 4r
         inv_s[i] = run;
         if (fe_is_zero_mod(d)) { s_m = i; }        // at most one i can match
         else fe_mul(run, run, d);
     }
-    tot_s[tid] = run;
-    __syncthreads();
 
-    // ---- phase B: invert the 256 thread totals (warp 0: 32 lanes x 8, then lane 0) ----
-    if (tid < 32) {
-        Fr pre[8], lrun;
-        fe_const<FrTag, FR_ONE>(lrun);
-        for (int k = 0; k < 8; k++) { pre[k] = lrun; fe_mul(lrun, lrun, tot_s[tid * 8 + k]); }
-        lane_s[tid] = lrun;
-        __syncwarp();
-        if (tid == 0) {
-            Fr lpre[32], g;
-            fe_const<FrTag, FR_ONE>(g);
-            for (int l = 0; l < 32; l++) { lpre[l] = g; fe_mul(g, g, lane_s[l]); }
-            Fr ginv;
-            fe_inv(ginv, g);
-            for (int l = 31; l >= 0; l--) {
-                Fr li;
-                fe_mul(li, ginv, lpre[l]);
-                fe_mul(ginv, ginv, lane_s[l]);
-                lane_s[l] = li;
+    // ---- phase B: 1 / T_t for the 256 thread totals T_t, in parallel ---------------------------
+    // 1/T_t = (1/G) * (product of every other total), G = product of all 256.  Within a warp the
+    // inclusive prefix and suffix products come from two Kogge-Stone scans over shuffles (5 steps,
+    // two independent products each); across the 8 warps, lane w of warp 0 forms the product of the
+    // other warps' totals, one lane inverts G, and every thread finishes with two products.  The
+    // dependent chain is ~20 products + one inversion (it was ~145 + one inversion with the
+    // serial fold), and warp 1 computes (z^4096 - 1) / 4096 meanwhile.
+    Fr pre = run, suf = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Fr up, dn;
+#pragma unroll
+        for (int i = 0; i < FR_N; i++) { up.v[i] = __shfl_up_sync(0xffffffffu, pre.v[i], d); dn.v[i] = __shfl_down_sync(0xffffffffu, suf.v[i], d); }
+        if (lane >= d) fe_mul(pre, pre, up);
+        if (lane + d < 32) fe_mul(suf, suf, dn);
+    }
+    if (lane == 31) wtot_s[wid] = pre;             // warp total
+    Fr excl_pre, excl_suf;                         // products of the totals of the lanes below / above
+#pragma unroll
+    for (int i = 0; i < FR_N; i++) { excl_pre.v[i] = __shfl_up_sync(0xffffffffu, pre.v[i], 1); excl_suf.v[i] = __shfl_down_sync(0xffffffffu, suf.v[i], 1); }
+    if (lane == 0) fe_const<FrTag, FR_ONE>(excl_pre);
+    if (lane == 31) fe_const<FrTag, FR_ONE>(excl_suf);
+    __syncthreads();
+    if (wid == 0) {
+        constexpr int NW = FR_THREADS / 32;
+        Fr others, wt;                             // lane w < 8: product of the other warps' totals
+        fe_const<FrTag, FR_ONE>(others);
+        fe_const<FrTag, FR_ONE>(wt);
+        if (lane < NW) {
+            wt = wtot_s[lane];
+            for (int v = 0; v < NW; v++) {
+                if (v == lane) continue;
+                Fr t = wtot_s[v];
+                fe_mul(others, others, t);
             }
         }
-        __syncwarp();
-        Fr linv = lane_s[tid];
-        for (int k = 7; k >= 0; k--) {
-            Fr ti, tv = tot_s[tid * 8 + k];
-            fe_mul(ti, linv, pre[k]);
-            fe_mul(linv, linv, tv);
-            tot_s[tid * 8 + k] = ti;
-        }
+        Fr g, ginv;
+        fe_mul(g, others, wt);                     // lane 0: G (every lane < 8 holds G, up to the lazy bound)
+        if (lane == 0) fe_inv(ginv, g); else fe_zero(ginv);
+        shfl_fr(ginv, ginv, 0);
+        if (lane < NW) { fe_mul(others, others, ginv); wtot_s[lane] = others; }   // cofactor of warp `lane`
+    } else if (wid == 1 && lane == 0) {
+        Fr zp = z, one, scale;
+        for (int k = 0; k < 12; k++) fe_sqr(zp, zp);          // z^4096
+        fe_const<FrTag, FR_ONE>(one);
+        fe_sub<FrTag, 2>(zp, zp, one);
+        fe_const<FrTag, FR_INV4096>(scale);
+        fe_mul(zp, zp, scale);
+        bc_s[3] = zp;
     }
     __syncthreads();
     const int m = s_m;
 
     // ---- phase C: per-element inverses, partial sum for y ------------------------------
-    Fr inv_run = tot_s[tid];
+    Fr inv_run;
+    {
+        Fr cof = wtot_s[wid];
+        fe_mul(inv_run, excl_pre, excl_suf);
+        fe_mul(inv_run, inv_run, cof);             // 1 / T_t
+    }
     Fr sum;
     fe_zero(sum);
     bool bad = false;
     for (int k = FR_PER_THREAD - 1; k >= 0; k--) {
-        const int i = k * FR_THREADS + tid;   // interleaved: coalesced loads, conflict-free smem
+        const int i = k * FR_THREADS + tid;
         Fr w = prm.roots_brp[i], d, inv_i;
         fe_sub<FrTag, 2>(d, z, w);
         if (i == m) {
             fe_zero(inv_i);                            // slot unused
         } else {
-            Fr pre = inv_s[i];
-            fe_mul(inv_i, inv_run, pre);
+            Fr pre_i = inv_s[i];
+            fe_mul(inv_i, inv_run, pre_i);
             fe_mul(inv_run, inv_run, d);
         }
         inv_s[i] = inv_i;
@@ -884,26 +931,15 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
         fe_add(sum, sum, t);                           // < 4096 * 1.1 r, fits 270 bits
     }
     if (bad) s_bad = 1;
-    // CTA reduction of `sum` through shared memory (reuse tot_s)
-    __syncthreads();
-    tot_s[tid] = sum;
-    __syncthreads();
+    cta_sum_fr(sum, wsum_s, tid);                      // thread 0 holds the total; includes a __syncthreads()
     if (tid == 0) {
-        Fr y, total;
-        fe_zero(total);
-        for (int k = 0; k < FR_THREADS; k++) fe_add(total, total, tot_s[k]);
+        Fr y;
         if (m >= 0) {
             Fr pc; bool g;
             fr_load_be(pc, g, bp + 32 * m);
             fe_to_mont(y, pc);
         } else {
-            Fr zp = z, one, scale;
-            for (int k = 0; k < 12; k++) fe_sqr(zp, zp);          // z^4096
-            fe_const<FrTag, FR_ONE>(one);
-            fe_sub<FrTag, 2>(zp, zp, one);
-            fe_const<FrTag, FR_INV4096>(scale);
-            fe_mul(zp, zp, scale);
-            fe_mul(y, total, zp);
+            fe_mul(y, sum, bc_s[3]);                   // sum * (z^4096 - 1) / 4096
         }
         bc_s[1] = y;
         Fr yc;
@@ -926,7 +962,7 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
     Fr sum_m;
     fe_zero(sum_m);
     for (int k = 0; k < FR_PER_THREAD; k++) {
-        const int i = k * FR_THREADS + tid;   // interleaved: coalesced loads, conflict-free smem
+        const int i = k * FR_THREADS + tid;
         if (i == m) continue;
         Fr pc, t, qc;
         bool g;
@@ -944,15 +980,12 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
         }
     }
     if (m >= 0) {                                      // uniform per CTA
-        __syncthreads();
-        tot_s[tid] = sum_m;
-        __syncthreads();
+        __syncthreads();                               // wsum_s is reused
+        cta_sum_fr(sum_m, wsum_s, tid);
         if (tid == 0) {
-            Fr total, zinv, qm, qc;
-            fe_zero(total);
-            for (int k = 0; k < FR_THREADS; k++) fe_add(total, total, tot_s[k]);
+            Fr zinv, qm, qc;
             fe_inv(zinv, z);
-            fe_mul(qm, total, zinv);                   // plain total times Montgomery 1/z: plain again, < r + epsilon
+            fe_mul(qm, sum_m, zinv);                   // plain total times Montgomery 1/z: plain again, < r + epsilon
             fe_neg<FrTag, 2>(qc, qm);                  // in (0, 2r]
             fe_cond_sub_mod<FrTag>(qc);
             fe_cond_sub_mod<FrTag>(qc);
@@ -961,7 +994,7 @@ __global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
     }
 }
 #endif  // RK_TU_PATH
-constexpr size_t FR_SMEM_BYTES = sizeof(Fr) * (FR_THREADS + 32 + 4);
+constexpr size_t FR_SMEM_BYTES = sizeof(Fr) * (8 + 8 + 4);
 
 // ---------------------------------------------------------------------------
 // Trusted-setup decoding
