@@ -119,6 +119,8 @@ struct DeviceCtx {
     uint64_t table_bytes = 0;
     Fr* roots = nullptr;
     G1Affine* g1_aff = nullptr;            // 4096 setup points, affine Montgomery
+    LineStep* g2_lines = nullptr;          // device 0 only: Miller-loop lines of [s]G2 and the G2 generator
+    bool pairing_lanes = true;             // RAIKO_KZG_PAIRING_LANES=0: single-thread pairing check
     cudaStream_t s_main = nullptr, s_sha = nullptr, s_in = nullptr, s_out = nullptr;
     int chunk = 0;
     int max_partials = 0;
@@ -225,7 +227,7 @@ void free_device(DeviceCtx* d) {
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         if (s.ev_out) cudaEventDestroy(s.ev_out);
     }
-    cudaFree(d->table); cudaFree(d->roots); cudaFree(d->g1_aff); cudaFree(d->aff_scratch);
+    cudaFree(d->table); cudaFree(d->roots); cudaFree(d->g1_aff); cudaFree(d->aff_scratch); cudaFree(d->g2_lines);
     if (d->s_main) cudaStreamDestroy(d->s_main);
     if (d->s_sha) cudaStreamDestroy(d->s_sha);
     if (d->s_in) cudaStreamDestroy(d->s_in);
@@ -661,7 +663,10 @@ rk_status run_shard(DeviceCtx* d, const BatchArgs& a) {
         const bool need_hash = a.mode == MODE_COMMIT_PROVE || a.mode == MODE_EVAL_ONLY || a.mode == MODE_POINT_ONLY || a.mode == MODE_PROVE_VH;
         if (need_hash) {
             // large chunks: hash first on the main stream; small (latency-bound) batches: beside the MSM
-            const bool serial = d->sha_serial && cnt >= d->sm_count * d->warps_per_sm;
+            // (never beside the MSM when the call pipelines several chunks: the hash of chunk i+1 then
+            // lands between the kernels of chunk i and holds SMs the persistent MSM kernel needs --
+            // measured 23 ms lost per 4736-blob chunk, profiles/r02/e2e_trace_8192.txt)
+            const bool serial = d->sha_serial && (cnt >= d->sm_count * d->warps_per_sm || sizes.size() > 1);
             cudaStream_t hs = serial ? d->s_main : d->s_sha;
             if (!serial) CUDA_TRY(cudaStreamWaitEvent(d->s_sha, s.ev_in, 0));
             timer_begin(d, hs, T_SHA);
@@ -826,56 +831,95 @@ rk_status run_batch(rk_kzg_ctx* ctx, BatchArgs a) {
 // ----------------------------------------------------------------------------------------
 constexpr size_t VERIFY_MAX_N = 16384;
 
-// d_c, d_p: n x 48 compressed; d_z, d_y: n x 32 big-endian canonical (all on the device).
-rk_status verify_core(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, int n, const uint8_t* d_c, const uint8_t* d_p,
-                      const uint8_t* d_z, const uint8_t* d_y, int* out_ok) {
+// Scratch and decompression stage of one verification call.  verify_begin() allocates, then
+// decompresses / subgroup-checks the commitments and proofs on the side stream (s_sha) -- they do
+// not depend on z or y, so they overlap the challenge / evaluation kernels of the blob path and the
+// transcript hash.  verify_finish() runs the rest on the main stream and joins.
+struct VerifyState {
+    int n = 0;
+    const uint8_t *d_c = nullptr, *d_p = nullptr;
     G1Affine *d_pts = nullptr, *d_pair = nullptr;
     int *d_inf = nullptr, *d_pinf = nullptr, *d_flags = nullptr;
-    G1Xyzz *d_a = nullptr, *d_e = nullptr;
-    Fr *d_t = nullptr, *d_r = nullptr;
+    G1Xyzz *d_a = nullptr, *d_e = nullptr, *d_part = nullptr;
+    Fr* d_r = nullptr;
     uint8_t* d_g2 = nullptr;
-    CUDA_TRY(buf.alloc(&d_pts, 2 * (size_t)n)); CUDA_TRY(buf.alloc(&d_inf, 2 * (size_t)n));
-    CUDA_TRY(buf.alloc(&d_a, (size_t)n)); CUDA_TRY(buf.alloc(&d_e, (size_t)n)); CUDA_TRY(buf.alloc(&d_t, (size_t)n));
-    CUDA_TRY(buf.alloc(&d_r, 1)); CUDA_TRY(buf.alloc(&d_pair, 2)); CUDA_TRY(buf.alloc(&d_pinf, 2));
-    CUDA_TRY(buf.alloc(&d_flags, 4)); CUDA_TRY(buf.alloc(&d_g2, 384));
+    cudaEvent_t ev_inputs = nullptr, ev_points = nullptr;
+    ~VerifyState() { if (ev_inputs) cudaEventDestroy(ev_inputs); if (ev_points) cudaEventDestroy(ev_points); }
+};
+constexpr int VR_PARTS = 64;               // CTAs of the first reduction level
+
+// d_c, d_p: n x 48 compressed, on the device; the copies that produced them were enqueued on s_main.
+rk_status verify_begin(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, VerifyState& v, int n, const uint8_t* d_c, const uint8_t* d_p) {
+    v.n = n; v.d_c = d_c; v.d_p = d_p;
+    CUDA_TRY(buf.alloc(&v.d_pts, 2 * (size_t)n)); CUDA_TRY(buf.alloc(&v.d_inf, 2 * (size_t)n));
+    CUDA_TRY(buf.alloc(&v.d_a, (size_t)n)); CUDA_TRY(buf.alloc(&v.d_e, 3 * (size_t)n)); CUDA_TRY(buf.alloc(&v.d_part, 2 * (size_t)VR_PARTS));
+    CUDA_TRY(buf.alloc(&v.d_r, 1)); CUDA_TRY(buf.alloc(&v.d_pair, 2)); CUDA_TRY(buf.alloc(&v.d_pinf, 2));
+    CUDA_TRY(buf.alloc(&v.d_flags, 4)); CUDA_TRY(buf.alloc(&v.d_g2, 384));
+    CUDA_TRY(cudaEventCreateWithFlags(&v.ev_inputs, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&v.ev_points, cudaEventDisableTiming));
+    cudaStream_t st = d->s_main, side = d->s_sha;
+    CUDA_TRY(cudaMemsetAsync(v.d_flags, 0, 4 * sizeof(int), st));
+    // [s]G2 then the generator (only the single-thread pairing kernel reads them)
+    CUDA_TRY(cudaMemcpyAsync(v.d_g2, ctx->g2_be.data() + 192, 192, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(v.d_g2 + 192, ctx->g2_be.data(), 192, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(v.ev_inputs, st));
+    CUDA_TRY(cudaStreamWaitEvent(side, v.ev_inputs, 0));
+    launch_k_g1_decompress_validate((n + 31) / 32, 32, 0, side, d_c, n, v.d_pts, v.d_inf, v.d_flags + 0);
+    launch_k_g1_decompress_validate((n + 31) / 32, 32, 0, side, d_p, n, v.d_pts + n, v.d_inf + n, v.d_flags + 1);
+    CUDA_TRY(cudaEventRecord(v.ev_points, side));
+    d->stats.total_launches += 2;
+    return RK_OK;
+}
+
+// d_z, d_y: n x 32 big-endian canonical, on the device, produced on s_main.
+rk_status verify_finish(rk_kzg_ctx* ctx, DeviceCtx* d, VerifyState& v, const uint8_t* d_z, const uint8_t* d_y, int* out_ok) {
+    (void)ctx;
+    const int n = v.n;
     cudaStream_t st = d->s_main;
-    CUDA_TRY(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), st));
-    // [s]G2 then the generator
-    CUDA_TRY(cudaMemcpyAsync(d_g2, ctx->g2_be.data() + 192, 192, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_g2 + 192, ctx->g2_be.data(), 192, cudaMemcpyHostToDevice, st));
     // RAIKO_KZG_VERIFY_TRACE=1 prints the per-stage device time of this call to stderr
     const bool trace = getenv("RAIKO_KZG_VERIFY_TRACE") != nullptr;
-    cudaEvent_t ev[7];
+    cudaEvent_t ev[6];
     if (trace) for (auto& e : ev) cudaEventCreate(&e);
     auto mark = [&](int i) { if (trace) cudaEventRecord(ev[i], st); };
     mark(0);
-    launch_k_g1_decompress_validate((n + 63) / 64, 64, 0, st, d_c, n, d_pts, d_inf, d_flags + 0);
-    launch_k_g1_decompress_validate((n + 63) / 64, 64, 0, st, d_p, n, d_pts + n, d_inf + n, d_flags + 1);
+    launch_k_batch_challenge(1, 64, 0, st, v.d_c, d_z, d_y, v.d_p, n, v.d_r);
     mark(1);
-    launch_k_batch_challenge(1, 1, 0, st, d_c, d_z, d_y, d_p, n, d_r);
+    CUDA_TRY(cudaStreamWaitEvent(st, v.ev_points, 0));
     mark(2);
-    launch_k_verify_terms((n + 63) / 64, 64, 0, st, d_r, d_z, d_y, d_pts, d_inf, d_pts + n, d_inf + n, n, d_a, d_e, d_t, d_flags + 2);
+    launch_k_verify_terms((4 * n + 63) / 64, 64, 0, st, v.d_r, d_z, d_y, v.d_pts, v.d_inf, v.d_pts + n, v.d_inf + n, n, v.d_a, v.d_e, v.d_flags + 2);
     mark(3);
-    launch_k_verify_reduce(1, VR_THREADS, 0, st, d_a, d_e, d_t, n, d_pair, d_pinf);
+    launch_k_verify_reduce_partial(VR_PARTS, VR_THREADS, 0, st, v.d_a, n, v.d_e, 3 * n, v.d_part, v.d_part + VR_PARTS);
+    launch_k_verify_reduce(1, VR_THREADS, 0, st, v.d_part, v.d_part + VR_PARTS, VR_PARTS, v.d_pair, v.d_pinf);
     mark(4);
-    launch_k_pairing_check(1, 1, 0, st, d_pair, d_pinf, d_g2, d_g2 + 192, d_flags + 3);
+    if (d->pairing_lanes && d->g2_lines) launch_k_pairing_check_lanes(1, 32, 0, st, v.d_pair, v.d_pinf, d->g2_lines, v.d_flags + 3);
+    else launch_k_pairing_check(1, 1, 0, st, v.d_pair, v.d_pinf, v.d_g2, v.d_g2 + 192, v.d_flags + 3);
     mark(5);
-    if (trace) {
-        cudaEventSynchronize(ev[5]);
-        const char* names[5] = {"decompress+subgroup", "batch challenge", "r-power terms", "reduce", "pairing"};
-        for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, "[verify n=%d] %-20s %8.3f ms\n", n, names[i], ms); }
-        for (auto& e : ev) cudaEventDestroy(e);
-    }
-    d->stats.total_launches += 6;
+    d->stats.total_launches += 5;
     CUDA_TRY(cudaGetLastError());
     int flags[4];
-    CUDA_TRY(cudaMemcpyAsync(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(flags, v.d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(d->s_sha));
+    if (trace) {
+        const char* names[5] = {"transcript hash", "wait for decompress+subgroup (side stream)", "r-power terms", "reduce", "pairing"};
+        for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, "[verify n=%d] %-44s %8.3f ms\n", n, names[i], ms); }
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     if (flags[0]) return fail(RK_ERR_BAD_POINT, "commitment %d is not a valid G1 point", flags[0] - 1);
     if (flags[1]) return fail(RK_ERR_BAD_POINT, "proof %d is not a valid G1 point", flags[1] - 1);
     if (flags[2]) return fail(RK_ERR_NONCANONICAL_FE, "z or y of element %d is not a canonical field element", flags[2] - 1);
     *out_ok = flags[3];
     return RK_OK;
+}
+
+rk_status verify_core(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, int n, const uint8_t* d_c, const uint8_t* d_p,
+                      const uint8_t* d_z, const uint8_t* d_y, int* out_ok) {
+    VerifyState v;
+    rk_status st = verify_begin(ctx, d, buf, v, n, d_c, d_p);
+    if (st != RK_OK) { cudaStreamSynchronize(d->s_main); cudaStreamSynchronize(d->s_sha); return st; }
+    st = verify_finish(ctx, d, v, d_z, d_y, out_ok);
+    if (st != RK_OK) { cudaStreamSynchronize(d->s_main); cudaStreamSynchronize(d->s_sha); }
+    return st;
 }
 
 rk_status verify_blob_batch_device(rk_kzg_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs,
@@ -899,6 +943,12 @@ rk_status verify_blob_batch_device(rk_kzg_ctx* ctx, const uint8_t* blobs, const 
     CUDA_TRY(cudaMemcpyAsync(d_c, commitments, 48 * n, cudaMemcpyDefault, st));
     CUDA_TRY(cudaMemcpyAsync(d_p, proofs, 48 * n, cudaMemcpyDefault, st));
     CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t) * n, st));
+    VerifyState v;                          // declared after buf: destroyed first
+    {
+        rk_status vst = verify_begin(ctx, d, buf, v, (int)n, d_c, d_p);     // decompression runs beside the loop below
+        if (vst != RK_OK) { cudaStreamSynchronize(st); cudaStreamSynchronize(d->s_sha); return vst; }
+    }
+    struct Join { DeviceCtx* d; ~Join() { cudaStreamSynchronize(d->s_main); cudaStreamSynchronize(d->s_sha); cudaStreamSynchronize(d->s_in); } } join{d};
     const size_t chunk = (size_t)d->chunk;
     for (size_t first = 0, ci = 0; first < n; first += chunk, ci++) {
         ChunkSlot& s = d->slot[ci & 1];
@@ -933,7 +983,7 @@ rk_status verify_blob_batch_device(rk_kzg_ctx* ctx, const uint8_t* blobs, const 
     timers_collect(d);
     for (size_t i = 0; i < n; i++)
         if (bad[i]) return fail(RK_ERR_NONCANONICAL_FE, "blob %zu: Failed to deserialize blob to field elements", i);
-    return verify_core(ctx, d, buf, (int)n, d_c, d_p, d_z, d_y, out_ok);
+    return verify_finish(ctx, d, v, d_z, d_y, out_ok);
 }
 
 rk_status check_blob_len(size_t len) {
@@ -995,6 +1045,29 @@ rk_status rk_kzg_ctx_create_ex(const uint8_t* settings, size_t len, const int* d
             return st;
         }
     ctx->geom = ctx->devs[0]->geom;
+    {
+        // fixed-argument pairing precomputation on the verification device (ctx device 0)
+        DeviceCtx* d = ctx->devs[0];
+        if (const char* e = getenv("RAIKO_KZG_PAIRING_LANES")) d->pairing_lanes = atoi(e) != 0;
+        rk_status st = RK_OK;
+        cudaError_t ce = cudaSetDevice(d->dev);
+        uint8_t* d_g2 = nullptr;
+        if (ce == cudaSuccess) ce = cudaMalloc(&d_g2, 384);
+        if (ce == cudaSuccess) ce = cudaMalloc(&d->g2_lines, PAIRING_LINES_BYTES);
+        if (ce == cudaSuccess) ce = cudaMemcpy(d_g2, ctx->g2_be.data() + 192, 192, cudaMemcpyHostToDevice);      // [s]G2
+        if (ce == cudaSuccess) ce = cudaMemcpy(d_g2 + 192, ctx->g2_be.data(), 192, cudaMemcpyHostToDevice);      // generator
+        if (ce == cudaSuccess) {
+            launch_k_pairing_precompute(1, 2, 0, 0, d_g2, d_g2 + 192, d->g2_lines);
+            ce = cudaDeviceSynchronize();
+        }
+        cudaFree(d_g2);
+        cudaSetDevice(prev);
+        if (ce != cudaSuccess) {
+            st = fail(RK_ERR_CUDA, "pairing precomputation failed: %s", cudaGetErrorString(ce));
+            rk_kzg_ctx_destroy(ctx);
+            return st;
+        }
+    }
     *out = ctx;
     return RK_OK;
 }

@@ -1356,126 +1356,159 @@ __device__ __forceinline__ bool fr_words_from_be_canon(uint32_t (&s)[8], const u
     return !scalar_geq_r(s);
 }
 
-// r = hash_to_bls_field(sha256("RCKZGBATCH___V1_" | be64(4096) | be64(n) | (C_i | z_i | y_i | proof_i)*)), one thread.
-// The transcript is a sequence of 16-byte-aligned fields, so it is fed word-wise (uint4 loads);
-// the chain itself is serial by construction.
-__global__ void k_batch_challenge(const uint8_t* c, const uint8_t* z, const uint8_t* y, const uint8_t* pr, int n, Fr* out_r) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// r = hash_to_bls_field(sha256("RCKZGBATCH___V1_" | be64(4096) | be64(n) | (C_i | z_i | y_i | proof_i)*)).
+// The chain over the 32 + 160 n transcript bytes is serial by construction (4096 tuples: 10 241
+// compressions), but only its 64 rounds per block are: the message schedule does not depend on the
+// chaining state.  One CTA of two warps: the 32 lanes of warp 1 gather and expand 32 consecutive
+// blocks (one each) into shared memory while lane 0 of warp 0 runs the rounds of the previous 32
+// (three-deep dependent chain per round, sha256_round).  33 ms -> ~7 ms for 4096 tuples.
+// Every field of the transcript is 16-byte aligned, so blocks are gathered as four uint4 loads.
+__device__ __forceinline__ uint4 transcript_quad(const uint8_t* c, const uint8_t* z, const uint8_t* y, const uint8_t* pr, int n, long long q) {
+    // q-th 16-byte unit of the transcript (q >= 0); units past the data are zero (padding is patched by the caller)
+    if (q < 2) {
+        if (q == 0) return make_uint4(0x5a4b4352u, 0x54414247u, 0x5f5f4843u, 0x5f31565fu);   // "RCKZGBATCH___V1_" as little-endian loads
+        return make_uint4(0u, __byte_perm(4096u, 0, 0x0123), 0u, __byte_perm((uint32_t)n, 0, 0x0123));
+    }
+    const long long u = q - 2;
+    const long long i = u / 10;
+    const int f = (int)(u - 10 * i);
+    if (i >= n) return make_uint4(0u, 0u, 0u, 0u);
+    const uint8_t* p = f < 3 ? c + 48 * i + 16 * f : f < 5 ? z + 32 * i + 16 * (f - 3) : f < 7 ? y + 32 * i + 16 * (f - 5) : pr + 48 * i + 16 * (f - 7);
+    return *reinterpret_cast<const uint4*>(p);
+}
+__global__ void __launch_bounds__(64) k_batch_challenge(const uint8_t* c, const uint8_t* z, const uint8_t* y, const uint8_t* pr, int n, Fr* out_r) {
+    __shared__ uint32_t wbuf[2][32][65];              // [parity][block in group][word], padded against bank conflicts
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long bytes = 32ll + 160ll * n;
+    const long long nblk = (bytes + 9 + 63) / 64;     // data | 0x80 | zeros | be64(bits)
+    const long long ngroups = (nblk + 31) / 32;
     Sha256State st;
     sha256_init(st);
-    uint32_t w[16];
-    int fill = 0;                                   // words in w
-    auto push_word = [&](uint32_t v) {
-        w[fill++] = v;
-        if (fill == 16) { sha256_compress(st, w); fill = 0; }
-    };
-    auto push16 = [&](const uint8_t* p, int quads) {    // quads x 16 bytes, 16-byte aligned
-        const uint4* q = reinterpret_cast<const uint4*>(p);
-        for (int i = 0; i < quads; i++) {
-            uint4 v = q[i];
-            push_word(__byte_perm(v.x, 0, 0x0123)); push_word(__byte_perm(v.y, 0, 0x0123));
-            push_word(__byte_perm(v.z, 0, 0x0123)); push_word(__byte_perm(v.w, 0, 0x0123));
+    for (long long g = 0; g <= ngroups; g++) {
+        if (warp == 1 && g < ngroups) {               // producer: block 32 g + lane
+            const long long b = 32 * g + lane;
+            if (b < nblk) {
+                uint32_t blk[16];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const long long off = 64 * b + 16 * q;
+                    uint4 v = off < bytes ? transcript_quad(c, z, y, pr, n, off / 16) : make_uint4(0u, 0u, 0u, 0u);
+                    blk[4 * q] = __byte_perm(v.x, 0, 0x0123); blk[4 * q + 1] = __byte_perm(v.y, 0, 0x0123);
+                    blk[4 * q + 2] = __byte_perm(v.z, 0, 0x0123); blk[4 * q + 3] = __byte_perm(v.w, 0, 0x0123);
+                }
+                // padding: the data ends on a 16-byte boundary (32 + 160 n), so 0x80 starts a word
+                const long long pad_word = bytes / 4 - 16 * b;          // word index of the 0x80 byte within this block
+                if (pad_word >= 0 && pad_word < 16) blk[pad_word] = 0x80000000u;
+                if (b == nblk - 1) { const unsigned long long bits = (unsigned long long)bytes * 8ull; blk[14] = (uint32_t)(bits >> 32); blk[15] = (uint32_t)bits; }
+                uint32_t w[64];
+                sha256_schedule(w, blk);
+#pragma unroll
+                for (int i = 0; i < 64; i++) wbuf[g & 1][lane][i] = w[i];
+            }
         }
-    };
-    // "RCKZGBATCH___V1_" | be64(4096) | be64(n)
-    push_word(0x52434b5au); push_word(0x47424154u); push_word(0x43485f5fu); push_word(0x5f56315fu);
-    push_word(0); push_word(4096u); push_word(0); push_word((uint32_t)n);
-    for (int i = 0; i < n; i++) {
-        push16(c + 48 * (size_t)i, 3); push16(z + 32 * (size_t)i, 2); push16(y + 32 * (size_t)i, 2); push16(pr + 48 * (size_t)i, 3);
+        if (warp == 0 && lane == 0 && g > 0) {        // consumer: the 32 blocks of group g - 1, in order
+            const long long b0 = 32 * (g - 1);
+            const int cnt = (int)(nblk - b0 < 32 ? nblk - b0 : 32);
+            for (int j = 0; j < cnt; j++) sha256_rounds(st, wbuf[(g - 1) & 1][j]);
+        }
+        __syncthreads();
     }
-    const uint64_t bits = (32ull + 160ull * (uint64_t)n) * 8ull;
-    push_word(0x80000000u);
-    while (fill != 14) push_word(0);
-    push_word((uint32_t)(bits >> 32));
-    push_word((uint32_t)bits);
-    uint8_t h[32];
-    for (int i = 0; i < 8; i++) store_be32(h + 4 * i, st.h[i]);
-    Fr rm, rc;
-    fr_from_be_reduce(rm, rc, h);
-    *out_r = rm;
+    if (threadIdx.x == 0) {
+        uint8_t h[32];
+        for (int i = 0; i < 8; i++) store_be32(h + 4 * i, st.h[i]);
+        Fr rm, rc;
+        fr_from_be_reduce(rm, rc, h);
+        *out_r = rm;
+    }
 }
 
-// Thread i: r^i, then  A_i = r^i * proof_i,  E_i = (r^i z_i) * proof_i + r^i * C_i,  t_i = r^i y_i.
+// One thread per (tuple i, term j): the four variable-base scalar multiplications of tuple i run on
+// four threads, so the launch's latency is ONE 255-bit double-and-add instead of three in a row (and
+// the [sum r^i y_i] G the reduction used to do alone is spread over the tuples):
+//   j = 0:  A_i  = r^i * proof_i                     -> out_a[i]
+//   j = 1:  E_i1 = (r^i z_i) * proof_i               -> out_e[3 i]
+//   j = 2:  E_i2 = r^i * C_i                         -> out_e[3 i + 1]
+//   j = 3:  E_i3 = -(r^i y_i) * G                    -> out_e[3 i + 2]
+// so that  sum A = sum r^i proof_i  and  sum E = sum r^i (C_i - y_i G + z_i proof_i).
 __global__ void __launch_bounds__(64) k_verify_terms(const Fr* r_mont, const uint8_t* z, const uint8_t* y, const G1Affine* cs,
                                                       const int* c_inf, const G1Affine* ps, const int* p_inf, int n, G1Xyzz* out_a,
-                                                      G1Xyzz* out_e, Fr* out_t, int* err) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                      G1Xyzz* out_e, int* err) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gid >> 2, j = gid & 3;
     if (i >= n) return;
-    uint32_t zw[8], yw[8];
-    if (!fr_words_from_be_canon(zw, z + 32 * (size_t)i) || !fr_words_from_be_canon(yw, y + 32 * (size_t)i)) atomicCAS(err, 0, i + 1);
-    Fr base = *r_mont, ri, zc, zm, yc, ym, t;
+    Fr base = *r_mont, ri, kc;
     fe_const<FrTag, FR_ONE>(ri);
     for (uint32_t e = (uint32_t)i; e; e >>= 1) {
         if (e & 1) fe_mul(ri, ri, base);
         fe_sqr(base, base);
     }
-    fe_unpack<FrTag>(zc, zw); fe_to_mont(zm, zc);
-    fe_unpack<FrTag>(yc, yw); fe_to_mont(ym, yc);
-    fe_mul(t, ri, ym);
-    out_t[i] = t;
-    Fr s2, k1c, k2c;
-    fe_mul(s2, ri, zm);
-    fe_from_mont(k1c, ri);
-    fe_from_mont(k2c, s2);
-    uint32_t k1[8], k2[8];
-    fe_pack<FrTag>(k1, k1c);
-    fe_pack<FrTag>(k2, k2c);
-    G1Xyzz a, e, d;
-    g1_set_inf(a); g1_set_inf(e);
-    if (!p_inf[i]) { g1_scalar_mul(a, ps[i], k1); g1_scalar_mul(e, ps[i], k2); }
-    if (!c_inf[i]) { g1_scalar_mul(d, cs[i], k1); g1_add(e, d); }
-    out_a[i] = a;
-    out_e[i] = e;
-}
-
-// One CTA: PL = sum A_i, ER = sum E_i - (sum t_i) * G; writes the two pairing inputs
-// (-PL, ER) as affine points with infinity flags.
-__global__ void __launch_bounds__(VR_THREADS) k_verify_reduce(const G1Xyzz* a, const G1Xyzz* e, const Fr* t, int n, G1Affine* out_pts, int* out_inf) {
-    __shared__ G1Xyzz sh[VR_THREADS];
-    __shared__ Fr sht[VR_THREADS];
-    const int tid = threadIdx.x;
-    G1Xyzz acc;
-    for (int pass = 0; pass < 2; pass++) {
-        const G1Xyzz* src = pass == 0 ? a : e;
-        g1_set_inf(acc);
-        for (int i = tid; i < n; i += VR_THREADS) { G1Xyzz p = src[i]; g1_add(acc, p); }
-        sh[tid] = acc;
-        __syncthreads();
-        for (int s = VR_THREADS / 2; s >= 1; s >>= 1) {
-            if (tid < s) { G1Xyzz p = sh[tid + s]; G1Xyzz q = sh[tid]; g1_add(q, p); sh[tid] = q; }
-            __syncthreads();
-        }
-        if (pass == 0) {
-            if (tid == 0) {
-                G1Xyzz pl = sh[0];
-                G1Affine aff;
-                out_inf[0] = !g1_xyzz_to_affine(aff, pl);
-                if (!out_inf[0]) { fe_neg<FpTag, 2>(aff.y, aff.y); out_pts[0] = aff; }
-            }
-            __syncthreads();
-        }
+    if (j == 1 || j == 3) {
+        uint32_t sw[8];
+        if (!fr_words_from_be_canon(sw, (j == 1 ? z : y) + 32 * (size_t)i)) atomicCAS(err, 0, i + 1);
+        Fr sc, sm;
+        fe_unpack<FrTag>(sc, sw); fe_to_mont(sm, sc);
+        fe_mul(ri, ri, sm);
     }
-    Fr ts;
-    fe_zero(ts);
-    for (int i = tid; i < n; i += VR_THREADS) fe_add(ts, ts, t[i]);       // n * 1.1 r must stay < 2^270 (n < 30 000); the host caps a call at VERIFY_MAX_N = 16384
-    sht[tid] = ts;
-    __syncthreads();
-    if (tid == 0) {
-        Fr total, tc;
-        fe_zero(total);
-        for (int k = 0; k < VR_THREADS; k++) fe_add(total, total, sht[k]);
-        fe_from_mont(tc, total);                                    // canonical sum of r^i y_i
-        uint32_t k[8];
-        fe_pack<FrTag>(k, tc);
+    fe_from_mont(kc, ri);
+    uint32_t k[8];
+    fe_pack<FrTag>(k, kc);
+    G1Xyzz t;
+    g1_set_inf(t);
+    if (j <= 1) { if (!p_inf[i]) g1_scalar_mul(t, ps[i], k); }
+    else if (j == 2) { if (!c_inf[i]) g1_scalar_mul(t, cs[i], k); }
+    else {
         G1Affine g;
         fe_const<FpTag, FP_GEN_X>(g.x); fe_const<FpTag, FP_GEN_Y>(g.y);
-        G1Xyzz yg, er = sh[0];
-        g1_scalar_mul(yg, g, k);
-        if (!g1_is_inf(yg)) fe_neg<FpTag, 6>(yg.y, yg.y);
-        g1_add(er, yg);
-        G1Affine aff;
-        out_inf[1] = !g1_xyzz_to_affine(aff, er);
-        if (!out_inf[1]) out_pts[1] = aff;
+        g1_scalar_mul(t, g, k);
+        if (!g1_is_inf(t)) fe_neg<FpTag, 6>(t.y, t.y);
+    }
+    if (j == 0) out_a[i] = t; else out_e[3 * (size_t)i + (j - 1)] = t;
+}
+
+// Sums of the terms, two levels.  Level 1: CTA b folds a strided slice of `src` (count points) into
+// part[b]; level 2 (one CTA): folds the two partial arrays and writes the pairing inputs
+// (-sum A, sum E) as affine points with infinity flags.
+__device__ __forceinline__ void cta_sum_g1(G1Xyzz& acc, G1Xyzz* sh, int tid) {
+    sh[tid] = acc;
+    __syncthreads();
+    for (int s = VR_THREADS / 2; s >= 1; s >>= 1) {
+        if (tid < s) { G1Xyzz p = sh[tid + s]; G1Xyzz q = sh[tid]; g1_add(q, p); sh[tid] = q; }
+        __syncthreads();
+    }
+    acc = sh[0];
+    __syncthreads();
+}
+__global__ void __launch_bounds__(VR_THREADS) k_verify_reduce_partial(const G1Xyzz* a, int na, const G1Xyzz* e, int ne, G1Xyzz* part_a, G1Xyzz* part_e) {
+    __shared__ G1Xyzz sh[VR_THREADS];
+    const int tid = threadIdx.x;
+    const int stride = gridDim.x * VR_THREADS;
+    for (int pass = 0; pass < 2; pass++) {
+        const G1Xyzz* src = pass == 0 ? a : e;
+        const int count = pass == 0 ? na : ne;
+        G1Xyzz acc;
+        g1_set_inf(acc);
+        for (int i = blockIdx.x * VR_THREADS + tid; i < count; i += stride) { G1Xyzz p = src[i]; g1_add(acc, p); }
+        cta_sum_g1(acc, sh, tid);
+        if (tid == 0) (pass == 0 ? part_a : part_e)[blockIdx.x] = acc;
+    }
+}
+__global__ void __launch_bounds__(VR_THREADS) k_verify_reduce(const G1Xyzz* part_a, const G1Xyzz* part_e, int nparts, G1Affine* out_pts, int* out_inf) {
+    __shared__ G1Xyzz sh[VR_THREADS];
+    const int tid = threadIdx.x;
+    for (int pass = 0; pass < 2; pass++) {
+        const G1Xyzz* src = pass == 0 ? part_a : part_e;
+        G1Xyzz acc;
+        g1_set_inf(acc);
+        for (int i = tid; i < nparts; i += VR_THREADS) { G1Xyzz p = src[i]; g1_add(acc, p); }
+        cta_sum_g1(acc, sh, tid);
+        if (tid == 0) {
+            G1Affine aff;
+            out_inf[pass] = !g1_xyzz_to_affine(aff, acc);
+            if (!out_inf[pass]) {
+                if (pass == 0) fe_neg<FpTag, 2>(aff.y, aff.y);      // -sum A pairs with [s]G2
+                out_pts[pass] = aff;
+            }
+        }
     }
 }
 
@@ -1485,7 +1518,8 @@ __global__ void __launch_bounds__(VR_THREADS) k_verify_reduce(const G1Xyzz* a, c
 #ifdef RK_TU_PAIRING
 #include "pairing.cuh"
 namespace rk {
-// e(pts[0], [s]G2) * e(pts[1], G2) == 1 ?   Single thread.
+// e(pts[0], [s]G2) * e(pts[1], G2) == 1 ?   Single thread: the obviously-correct reference path
+// (RAIKO_KZG_PAIRING_LANES=0), kept as the A/B partner of the lane-parallel kernel below.
 __global__ void k_pairing_check(const G1Affine* pts, const int* inf, const uint8_t* g2_s_be, const uint8_t* g2_gen_be, int* out_ok) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     G2Affine qs[2];
@@ -1494,6 +1528,39 @@ __global__ void k_pairing_check(const G1Affine* pts, const int* inf, const uint8
     G1Affine ps[2] = {pts[0], pts[1]};
     int pinf[2] = {inf[0], inf[1]};
     *out_ok = pairing_product_is_one<2>(ps, pinf, qs) ? 1 : 0;
+}
+
+// Once per context: the Miller-loop lines of the two fixed G2 arguments ([s]G2, then the generator),
+// thread q handles point q.  out: 2 x PAIRING_STEPS LineStep.
+__global__ void k_pairing_precompute(const uint8_t* g2_s_be, const uint8_t* g2_gen_be, LineStep* out) {
+    const int q = threadIdx.x;
+    if (blockIdx.x != 0 || q >= 2) return;
+    G2Affine pt;
+    g2_from_be192(pt, q == 0 ? g2_s_be : g2_gen_be);
+    pairing_precompute_lines(out + q * PAIRING_STEPS, pt);
+}
+
+// The same check on the 12 low lanes of one warp (pairing.cuh, second half): lane k owns coefficient
+// k of every Fp12 value, coefficients are exchanged through shared memory, G2 lines are precomputed.
+struct WarpLanes {
+    static constexpr int LANES = 1;
+    static constexpr unsigned MASK = 0xfffu;
+    Fp* sh;                                            // [4][12]
+    int k;
+    __device__ __forceinline__ int lane(int) const { return k; }
+    __device__ __forceinline__ void publish(int s, int kk, const Fp& v) { sh[s * 12 + kk] = v; }
+    __device__ __forceinline__ void sync() { __syncwarp(MASK); }
+    __device__ __forceinline__ const Fp* read(int s) const { return sh + s * 12; }
+};
+__global__ void __launch_bounds__(32) k_pairing_check_lanes(const G1Affine* pts, const int* inf, const LineStep* lines, int* out_ok) {
+    __shared__ Fp sh[48];
+    const int lane = threadIdx.x;
+    if (blockIdx.x != 0 || lane >= 12) return;         // lanes 12..31 leave; every sync below names lanes 0..11
+    G1Affine ps[2] = {pts[0], pts[1]};
+    int pinf[2] = {inf[0], inf[1]};
+    WarpLanes x{sh, lane};
+    const bool ok = lane_pairing_product_is_one(x, ps, pinf, lines, lines + PAIRING_STEPS);
+    if (lane == 0) *out_ok = ok ? 1 : 0;
 }
 
 }  // namespace rk

@@ -6,6 +6,9 @@
 
 namespace rk {
 
+struct LineStep;                                   // pairing.cuh (only the verify / pairing units see its definition)
+constexpr size_t PAIRING_LINES_BYTES = 2 * 68 * 4 * sizeof(Fp);   // 2 fixed G2 points x PAIRING_STEPS x LineStep
+
 #define RK_UNPAREN(...) __VA_ARGS__
 
 #define RK_KERNELS_MSM(X)                                                                      \
@@ -41,12 +44,15 @@ namespace rk {
     X(k_sha_fs_challenge, (const uint8_t* blobs, const uint8_t* commitments, int nblobs, uint8_t* out_z), (blobs, commitments, nblobs, out_z)) \
     X(k_g1_decompress_validate, (const uint8_t* in, int n, G1Affine* out, int* out_inf, int* err), (in, n, out, out_inf, err)) \
     X(k_batch_challenge, (const uint8_t* c, const uint8_t* z, const uint8_t* y, const uint8_t* pr, int n, Fr* out_r), (c, z, y, pr, n, out_r)) \
-    X(k_verify_terms, (const Fr* r_mont, const uint8_t* z, const uint8_t* y, const G1Affine* cs, const int* c_inf, const G1Affine* ps, const int* p_inf, int n, G1Xyzz* out_a, G1Xyzz* out_e, Fr* out_t, int* err), \
-      (r_mont, z, y, cs, c_inf, ps, p_inf, n, out_a, out_e, out_t, err))                       \
-    X(k_verify_reduce, (const G1Xyzz* a, const G1Xyzz* e, const Fr* t, int n, G1Affine* out_pts, int* out_inf), (a, e, t, n, out_pts, out_inf))
+    X(k_verify_terms, (const Fr* r_mont, const uint8_t* z, const uint8_t* y, const G1Affine* cs, const int* c_inf, const G1Affine* ps, const int* p_inf, int n, G1Xyzz* out_a, G1Xyzz* out_e, int* err), \
+      (r_mont, z, y, cs, c_inf, ps, p_inf, n, out_a, out_e, err))                              \
+    X(k_verify_reduce_partial, (const G1Xyzz* a, int na, const G1Xyzz* e, int ne, G1Xyzz* part_a, G1Xyzz* part_e), (a, na, e, ne, part_a, part_e)) \
+    X(k_verify_reduce, (const G1Xyzz* part_a, const G1Xyzz* part_e, int nparts, G1Affine* out_pts, int* out_inf), (part_a, part_e, nparts, out_pts, out_inf))
 
 #define RK_KERNELS_PAIRING(X)                                                                  \
-    X(k_pairing_check, (const G1Affine* pts, const int* inf, const uint8_t* g2_s_be, const uint8_t* g2_gen_be, int* out_ok), (pts, inf, g2_s_be, g2_gen_be, out_ok))
+    X(k_pairing_check, (const G1Affine* pts, const int* inf, const uint8_t* g2_s_be, const uint8_t* g2_gen_be, int* out_ok), (pts, inf, g2_s_be, g2_gen_be, out_ok)) \
+    X(k_pairing_precompute, (const uint8_t* g2_s_be, const uint8_t* g2_gen_be, LineStep* out), (g2_s_be, g2_gen_be, out)) \
+    X(k_pairing_check_lanes, (const G1Affine* pts, const int* inf, const LineStep* lines, int* out_ok), (pts, inf, lines, out_ok))
 
 #define RK_DECLARE_LAUNCH(name, params, args) \
     void launch_##name(dim3 grid, dim3 block, size_t smem, cudaStream_t st, RK_UNPAREN params);

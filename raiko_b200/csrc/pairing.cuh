@@ -382,3 +382,287 @@ RK_HD void g2_from_be192(G2Affine& q, const uint8_t* in) {
 RK_HD void g2_neg(G2Affine& r, const G2Affine& q) { r = q; fp2_neg(r.y, q.y); }
 
 }  // namespace rk
+
+namespace rk {
+// ===========================================================================
+// Lane-parallel formulation of the same pairing check (BASELINE.json configs[4] is a
+// throughput path: the single-thread check above cost 65-127 ms of a 150 ms batch verify).
+//
+// One warp; lane k < 12 owns coefficient k of every Fp12 value.  An Fp12 product is 144 Fp
+// products: lane k forms the two raw coefficients t[k] and t[k + 12] (12 products, perfectly
+// balanced: k + 1 and 11 - k terms), the fold modulo w^12 = 2 w^6 - 2 is a closed form per lane.
+// Squares take 7 products per lane, a sparse line multiplication 5, a Frobenius map 2.
+// The two G2 arguments of a KZG check are constants of the trusted setup ([s]G2 and the
+// generator), so the Miller loop's line slopes are precomputed once per context
+// (pairing_precompute_lines: 68 steps per point) and the loop itself has no G2 arithmetic left.
+// Fp12 inversion uses the norm maps Fp12 -> Fp6 -> Fp2 -> Fp (one Fp inversion) instead of the
+// 12 x 12 elimination.  The per-lane functions below are plain RK_HD code: the device kernel runs
+// them on the lanes of a warp with shared-memory exchange, the host tests run them in a loop over
+// k and compare every operation with the scalar implementation above.
+// ===========================================================================
+constexpr int PAIRING_STEPS = 68;                  // 63 doublings + 5 additions for |x| = 0xd201000000010000
+
+struct LineStep { Fp l0, l6, a, b; };              // line = l0 + l6 w^6 + (a xP) w^2 + (b xP) w^8 + yP w^3
+
+// lane k: raw coefficients t[k] (lo) and t[k + 12] (hi) of a * b
+RK_HD void fp12_mul_lane(int k, const Fp* a, const Fp* b, Fp& lo, Fp& hi) {
+    fe_zero(lo); fe_zero(hi);
+    for (int i = 0; i < 12; i++) {
+        Fp m;
+        if (i <= k) { fe_mul(m, a[i], b[k - i]); fq_add(lo, lo, m); }
+        else { fe_mul(m, a[i], b[k + 12 - i]); fq_add(hi, hi, m); }
+    }
+}
+// lane k: the same for a * a, cross terms once and doubled (7 products)
+RK_HD void fp12_sqr_lane(int k, const Fp* a, Fp& lo, Fp& hi) {
+    fe_zero(lo); fe_zero(hi);
+    for (int pass = 0; pass < 2; pass++) {
+        const int n = pass == 0 ? k : k + 12;
+        Fp& t = pass == 0 ? lo : hi;
+        const int i0 = n > 11 ? n - 11 : 0;
+        for (int i = i0; 2 * i <= n; i++) {
+            const int j = n - i;
+            Fp m;
+            if (i == j) fe_sqr(m, a[i]);
+            else { fe_mul(m, a[i], a[j]); fq_dbl(m, m); }
+            fq_add(t, t, m);
+        }
+    }
+}
+// lane k: the same for a * (l0 + l2 w^2 + l3 w^3 + l6 w^6 + l8 w^8) (5 products)
+RK_HD void fp12_line_lane(int k, const Fp* a, const LineCoeffs& l, Fp& lo, Fp& hi) {
+    fe_zero(lo); fe_zero(hi);
+    const int es[5] = {0, 2, 3, 6, 8};
+    for (int q = 0; q < 5; q++) {
+        const int e = es[q];
+        const Fp& c = e == 0 ? l.l0 : e == 2 ? l.l2 : e == 3 ? l.l3 : e == 6 ? l.l6 : l.l8;
+        Fp m;
+        if (e <= k) { fe_mul(m, a[k - e], c); fq_add(lo, lo, m); }
+        else { fe_mul(m, a[k + 12 - e], c); fq_add(hi, hi, m); }
+    }
+}
+// lane k: coefficient k after folding t[0..22] (t[23] ignored) modulo w^12 = 2 w^6 - 2.
+//   w^(12+j) = 2 w^(6+j) - 2 w^j            (j <= 5)
+//   w^(12+j) = 2 w^j - 4 w^(j-6)            (6 <= j <= 10)
+RK_HD void fp12_fold_lane(int k, const Fp* t, Fp& out) {
+    Fp r = t[k], d;
+    if (k <= 5) {
+        fq_dbl(d, t[12 + k]); fq_sub(r, r, d);                         // - 2 T_k
+        if (k <= 4) { fq_dbl(d, t[18 + k]); fq_dbl(d, d); fq_sub(r, r, d); }   // - 4 T_(k+6)
+    } else {
+        fq_dbl(d, t[6 + k]); fq_add(r, r, d);                          // + 2 T_(k-6)
+        if (k <= 10) { fq_dbl(d, t[12 + k]); fq_add(r, r, d); }        // + 2 T_k
+    }
+    out = r;
+}
+// lane k: coefficient k of a^(p^e) (TAB = FP12_FROB1 / FP12_FROB2): two products
+template <class TAB>
+RK_HD void fp12_frob_lane(int k, const Fp* a, Fp& out) {
+    const int half = k >= 6 ? 13 : 0;
+    Fp acc;
+    fe_zero(acc);
+    for (int q = 0; q < 2; q++) {
+        const int j = (k % 6) + 6 * q;
+        Fp c, m;
+        for (int l = 0; l < FP_N; l++) c.v[l] = frob_word<TAB>(j * 26 + half + l);
+        fe_mul(m, a[j], c);
+        fq_add(acc, acc, m);
+    }
+    out = acc;
+}
+// the lines of the Miller loop for a FIXED G2 argument q (affine, on the twist, prime order)
+RK_HD_NOINLINE void pairing_precompute_lines(LineStep* out /* [PAIRING_STEPS] */, const G2Affine& q) {
+    G2Affine t = q;
+    const uint64_t e = ((uint64_t)BLS_X_ABS_W32::at(1) << 32) | BLS_X_ABS_W32::at(0);
+    int idx = 0;
+    auto emit = [&](const Fp2& lam, const Fp2& xt, const Fp2& yt) {
+        Fp2 c0;
+        fp2_mul(c0, lam, xt);
+        fp2_sub(c0, c0, yt);                       // lam xT - yT = a + b i -> (a - b) + b w^6
+        LineStep& s = out[idx++];
+        fq_sub(s.l0, c0.c0, c0.c1); s.l6 = c0.c1;
+        Fp d;
+        fq_sub(d, lam.c0, lam.c1);                 // -lam xP = (-(lam0 - lam1) xP) w^2 + (-lam1 xP) w^8
+        fq_neg(s.a, d); fe_cond_sub_k<2>(s.a);
+        fq_neg(s.b, lam.c1); fe_cond_sub_k<2>(s.b);
+    };
+    for (int bit = 62; bit >= 0; bit--) {
+        Fp2 num, den, lam, x3, y3;
+        fp2_sqr(num, t.x);
+        fp2_add(den, num, num); fp2_add(num, den, num);            // 3 x^2
+        fp2_add(den, t.y, t.y);
+        fp2_inv(den, den);
+        fp2_mul(lam, num, den);
+        emit(lam, t.x, t.y);
+        fp2_sqr(x3, lam); fp2_sub(x3, x3, t.x); fp2_sub(x3, x3, t.x);
+        fp2_sub(y3, t.x, x3); fp2_mul(y3, lam, y3); fp2_sub(y3, y3, t.y);
+        t.x = x3; t.y = y3;
+        if ((e >> bit) & 1) {
+            fp2_sub(num, q.y, t.y);
+            fp2_sub(den, q.x, t.x);
+            fp2_inv(den, den);
+            fp2_mul(lam, num, den);
+            emit(lam, t.x, t.y);
+            fp2_sqr(x3, lam); fp2_sub(x3, x3, t.x); fp2_sub(x3, x3, q.x);
+            fp2_sub(y3, t.x, x3); fp2_mul(y3, lam, y3); fp2_sub(y3, y3, t.y);
+            t.x = x3; t.y = y3;
+        }
+    }
+}
+
+// ---- the check itself, written once against an "exchange" policy X: -------------------------
+//   X::lanes()            how many lanes this invocation runs (device: 1 = this thread; host: 12)
+//   X::lane(i)            lane index of the i-th of them
+//   X::publish(slot, k, v) / X::sync() / X::read(slot) -> const Fp*   the 12-coefficient exchange
+// Device: lanes are threads, slots live in shared memory, sync = __syncwarp.  Host: one thread
+// plays all 12 lanes phase by phase.  A distributed Fp12 value is `Fp v[X::lanes()]`.
+template <class X>
+struct LaneFp12 {
+    Fp c[X::LANES];
+};
+template <class X> RK_HD void lp_mul(X& x, LaneFp12<X>& r, const LaneFp12<X>& a, const LaneFp12<X>& b) {
+    for (int i = 0; i < X::LANES; i++) { x.publish(0, x.lane(i), a.c[i]); x.publish(1, x.lane(i), b.c[i]); }
+    x.sync();
+    for (int i = 0; i < X::LANES; i++) { Fp lo, hi; fp12_mul_lane(x.lane(i), x.read(0), x.read(1), lo, hi); x.publish(2, x.lane(i), lo); x.publish(3, x.lane(i), hi); }
+    x.sync();
+    for (int i = 0; i < X::LANES; i++) fp12_fold_lane(x.lane(i), x.read(2), r.c[i]);
+    x.sync();
+}
+template <class X> RK_HD void lp_sqr(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
+    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
+    x.sync();
+    for (int i = 0; i < X::LANES; i++) { Fp lo, hi; fp12_sqr_lane(x.lane(i), x.read(0), lo, hi); x.publish(2, x.lane(i), lo); x.publish(3, x.lane(i), hi); }
+    x.sync();
+    for (int i = 0; i < X::LANES; i++) fp12_fold_lane(x.lane(i), x.read(2), r.c[i]);
+    x.sync();
+}
+template <class X> RK_HD void lp_line(X& x, LaneFp12<X>& r, const LaneFp12<X>& a, const LineCoeffs& l) {
+    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
+    x.sync();
+    for (int i = 0; i < X::LANES; i++) { Fp lo, hi; fp12_line_lane(x.lane(i), x.read(0), l, lo, hi); x.publish(2, x.lane(i), lo); x.publish(3, x.lane(i), hi); }
+    x.sync();
+    for (int i = 0; i < X::LANES; i++) fp12_fold_lane(x.lane(i), x.read(2), r.c[i]);
+    x.sync();
+}
+template <class TAB, class X> RK_HD void lp_frob(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
+    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
+    x.sync();
+    for (int i = 0; i < X::LANES; i++) fp12_frob_lane<TAB>(x.lane(i), x.read(0), r.c[i]);
+    x.sync();
+}
+template <class X> RK_HD void lp_conj(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
+    for (int i = 0; i < X::LANES; i++) { if (x.lane(i) & 1) fq_neg(r.c[i], a.c[i]); else r.c[i] = a.c[i]; }
+}
+template <class X> RK_HD void lp_pow_x(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
+    LaneFp12<X> acc = a;
+    const uint64_t e = ((uint64_t)BLS_X_ABS_W32::at(1) << 32) | BLS_X_ABS_W32::at(0);
+    for (int bit = 62; bit >= 0; bit--) {
+        lp_sqr(x, acc, acc);
+        if ((e >> bit) & 1) lp_mul(x, acc, acc, a);
+    }
+    r = acc;
+}
+// 1 / a through the norm maps: with q = p^6, N6 = a * a^q lies in Fp6; N2 = N6 * N6^(p^2) * N6^(p^4)
+// lies in Fp2 = {x + y w^6}; its inverse is ((x + 2y) - y w^6) / (x^2 + 2xy + 2y^2) because the
+// conjugate of w^6 = 1 + i is 2 - w^6.  1/a = a^q * N6^(p^2) * N6^(p^4) / N2.  One Fp inversion.
+// Returns false when a = 0.
+template <class X> RK_HD bool lp_inv(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
+    LaneFp12<X> aq, n6, f2, f4, m, n2;
+    lp_conj(x, aq, a);
+    lp_mul(x, n6, a, aq);
+    lp_frob<FP12_FROB2>(x, f2, n6);
+    lp_frob<FP12_FROB2>(x, f4, f2);
+    lp_mul(x, m, f2, f4);
+    lp_mul(x, n2, n6, m);                                   // = x + y w^6, every other coefficient 0
+    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), n2.c[i]);
+    x.sync();
+    const Fp* n = x.read(0);
+    Fp xx = n[0], yy = n[6], t, u, den, dinv;
+    fe_sqr(t, xx);                                          // x^2
+    fq_add(u, xx, yy); fq_dbl(u, u);                        // 2x + 2y
+    fe_mul(den, yy, u);
+    fq_add(den, den, t);                                    // x^2 + 2xy + 2y^2
+    fe_cond_sub_k<2>(t);
+    x.sync();
+    if (fq_is_zero(den)) return false;
+    fe_inv(dinv, den);
+    Fp i0, i6;                                              // inverse of n2: i0 + i6 w^6
+    fq_add(u, xx, yy); fq_add(u, u, yy);
+    fe_mul(i0, u, dinv); fe_cond_sub_k<2>(i0);
+    fe_mul(i6, yy, dinv); fq_neg(i6, i6); fe_cond_sub_k<2>(i6);
+    LaneFp12<X> am;
+    lp_mul(x, am, aq, m);
+    // (am) * (i0 + i6 w^6): a two-term sparse product, done as a general product with a sparse operand
+    LaneFp12<X> sp;
+    for (int i = 0; i < X::LANES; i++) { fe_zero(sp.c[i]); if (x.lane(i) == 0) sp.c[i] = i0; if (x.lane(i) == 6) sp.c[i] = i6; }
+    lp_mul(x, r, am, sp);
+    return true;
+}
+template <class X> RK_HD bool lp_is_one(X& x, const LaneFp12<X>& a) {
+    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
+    x.sync();
+    const Fp* c = x.read(0);
+    Fp one;
+    fe_const<FpTag, FP_ONE>(one);
+    bool ok = fq_eq(c[0], one);
+    for (int k = 1; k < 12; k++) ok = ok && fq_is_zero(c[k]);
+    x.sync();
+    return ok;
+}
+// e(P_0, Q_0) * e(P_1, Q_1) == 1 with the lines of Q_0, Q_1 precomputed (lines[pair][step]).
+template <class X>
+RK_HD bool lane_pairing_product_is_one(X& x, const G1Affine* ps, const int* p_inf, const LineStep* lines0, const LineStep* lines1) {
+    LaneFp12<X> f;
+    for (int i = 0; i < X::LANES; i++) { fe_zero(f.c[i]); if (x.lane(i) == 0) fe_const<FpTag, FP_ONE>(f.c[i]); }
+    const uint64_t e = ((uint64_t)BLS_X_ABS_W32::at(1) << 32) | BLS_X_ABS_W32::at(0);
+    int idx = 0;
+    auto apply = [&](int step) {
+        for (int k = 0; k < 2; k++) {
+            if (p_inf[k]) continue;
+            const LineStep& s = (k == 0 ? lines0 : lines1)[step];
+            LineCoeffs l;
+            l.l0 = s.l0; l.l6 = s.l6; l.l3 = ps[k].y;
+            fe_mul(l.l2, s.a, ps[k].x); fe_cond_sub_k<2>(l.l2);
+            fe_mul(l.l8, s.b, ps[k].x); fe_cond_sub_k<2>(l.l8);
+            lp_line(x, f, f, l);
+        }
+    };
+    for (int bit = 62; bit >= 0; bit--) {
+        lp_sqr(x, f, f);
+        apply(idx++);
+        if ((e >> bit) & 1) apply(idx++);
+    }
+    // final exponentiation, as final_exp_is_one above
+    LaneFp12<X> inv, t, f2, a, b, c, d;
+    if (!lp_inv(x, inv, f)) return false;
+    lp_conj(x, t, f);
+    lp_mul(x, t, t, inv);
+    lp_frob<FP12_FROB2>(x, f2, t);
+    lp_mul(x, f2, f2, t);
+    lp_pow_x(x, a, f2); lp_mul(x, a, a, f2); lp_conj(x, a, a);
+    lp_pow_x(x, b, a);  lp_mul(x, b, b, a);  lp_conj(x, b, b);
+    lp_pow_x(x, c, b); lp_conj(x, c, c);
+    lp_frob<FP12_FROB1>(x, t, b);
+    lp_mul(x, c, c, t);
+    lp_pow_x(x, d, c); lp_pow_x(x, d, d);
+    lp_frob<FP12_FROB2>(x, t, c);
+    lp_mul(x, d, d, t);
+    lp_conj(x, t, c);
+    lp_mul(x, d, d, t);
+    lp_sqr(x, t, f2);
+    lp_mul(x, t, t, f2);
+    lp_mul(x, d, d, t);
+    return lp_is_one(x, d);
+}
+
+// host / single-thread exchange: one thread plays all 12 lanes
+struct HostLanes {
+    static constexpr int LANES = 12;
+    Fp slot[4][12];                                // slots 2 and 3 are read as one 24-entry array (t[0..23])
+    RK_HD int lane(int i) const { return i; }
+    RK_HD void publish(int s, int k, const Fp& v) { slot[s][k] = v; }
+    RK_HD void sync() {}
+    RK_HD const Fp* read(int s) const { return slot[s]; }
+};
+
+}  // namespace rk

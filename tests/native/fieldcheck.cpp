@@ -116,4 +116,56 @@ int fc_verify_kzg_proof(const uint8_t* c48, const uint8_t* z32, const uint8_t* y
     g2_from_be192(qs[0], g2_gen); g2_from_be192(qs[1], g2_s);
     return pairing_product_is_one<2>(ps, inf, qs) ? 1 : 0;
 }
+// ---- lane-parallel pairing (pairing.cuh, second half) against the scalar implementation -------
+static void rand_fp12(Fp12& a, uint32_t seed) {
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 12345;
+    for (int k = 0; k < 12; k++) {
+        Fp c;
+        for (int i = 0; i < FP_N; i++) { s = s * 6364136223846793005ull + 1442695040888963407ull; c.v[i] = (uint32_t)(s >> 33) & LIMB_MASK; }
+        c.v[FP_N - 1] &= 0x7ffff;                        // < 2^379 < p
+        a.c[k] = c;
+    }
+}
+static bool fp12_same(const Fp12& a, const Fp12& b) { for (int k = 0; k < 12; k++) if (!fq_eq(a.c[k], b.c[k])) return false; return true; }
+static void to_lanes(LaneFp12<HostLanes>& l, const Fp12& a) { for (int k = 0; k < 12; k++) l.c[k] = a.c[k]; }
+static void from_lanes(Fp12& a, const LaneFp12<HostLanes>& l) { for (int k = 0; k < 12; k++) a.c[k] = l.c[k]; }
+// returns 0 when every lane-parallel Fp12 operation equals the scalar one on `iters` random inputs,
+// else a code naming the first operation that differs
+int fc_lane_fp12_ops(int iters) {
+    HostLanes x;
+    for (int it = 0; it < iters; it++) {
+        Fp12 a, b, want, got;
+        rand_fp12(a, 2 * it + 1); rand_fp12(b, 2 * it + 2);
+        LaneFp12<HostLanes> la, lb, lr;
+        to_lanes(la, a); to_lanes(lb, b);
+        fp12_mul(want, a, b); lp_mul(x, lr, la, lb); from_lanes(got, lr); if (!fp12_same(want, got)) return 1;
+        fp12_sqr(want, a); lp_sqr(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 2;
+        LineCoeffs l; l.l0 = b.c[0]; l.l2 = b.c[1]; l.l3 = b.c[2]; l.l6 = b.c[3]; l.l8 = b.c[4];
+        fp12_mul_line(want, a, l); lp_line(x, lr, la, l); from_lanes(got, lr); if (!fp12_same(want, got)) return 3;
+        fp12_frob<FP12_FROB1>(want, a); lp_frob<FP12_FROB1>(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 4;
+        fp12_frob<FP12_FROB2>(want, a); lp_frob<FP12_FROB2>(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 5;
+        fp12_conj(want, a); lp_conj(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 6;
+        if (!fp12_inv(want, a)) return 7;
+        if (!lp_inv(x, lr, la)) return 8;
+        from_lanes(got, lr); if (!fp12_same(want, got)) return 9;
+        if (it < 2) { fp12_pow_x(want, a); lp_pow_x(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 10; }
+    }
+    Fp12 z; for (int k = 0; k < 12; k++) fe_zero(z.c[k]);
+    LaneFp12<HostLanes> lz, lr; to_lanes(lz, z);
+    if (lp_inv(x, lr, lz)) return 11;                    // 0 has no inverse
+    return 0;
+}
+// the same check as fc_pairing_check2 through the lane-parallel path with precomputed lines
+int fc_pairing_check2_lanes(const uint8_t* p1, const uint8_t* q1, const uint8_t* p2, const uint8_t* q2) {
+    G1Affine ps[2]; int inf[2]; G2Affine qs[2];
+    int rc = g1_decompress(ps[0], p1); if (rc < 0) return -1; inf[0] = rc == 1;
+    rc = g1_decompress(ps[1], p2); if (rc < 0) return -1; inf[1] = rc == 1;
+    g2_from_be192(qs[0], q1); g2_from_be192(qs[1], q2);
+    if (!g2_on_curve(qs[0]) || !g2_on_curve(qs[1])) return -2;
+    static LineStep l0[PAIRING_STEPS], l1[PAIRING_STEPS];
+    pairing_precompute_lines(l0, qs[0]);
+    pairing_precompute_lines(l1, qs[1]);
+    HostLanes x;
+    return lane_pairing_product_is_one(x, ps, inf, l0, l1) ? 1 : 0;
+}
 }

@@ -177,3 +177,37 @@ def test_affine_batch_addition_pieces(L, pyoracle):
     for a, b in ((accs[0], accs[0]), (accs[1], o.g1_neg(accs[1])), (accs[2], pts[2])):
         assert L.fc_g1_affine_add_slow(o.g1_compress(a), o.g1_compress(b), one) == 0
         assert one.raw == o.g1_compress(o.g1_add(a, b))
+
+
+def test_lane_parallel_fp12_equals_scalar(L):
+    """pairing.cuh's lane-parallel Fp12 arithmetic (what k_pairing_check_lanes runs on 12 lanes of a
+    warp) against the scalar implementation, operation by operation: product, square, sparse line
+    product, both Frobenius maps, conjugation, the norm-based inversion (vs 12 x 12 elimination),
+    exponentiation by |x|; 0 has no inverse."""
+    assert L.fc_lane_fp12_ops(40) == 0
+
+
+def test_lane_parallel_pairing_check(L, pyoracle, golden):
+    """The KZG check e(C - yG + z proof, G2) e(-proof, [s]G2) == 1 through the lane-parallel path
+    with precomputed G2 lines: accepts the reference's own vector (eip4844.rs:162-184: k % 64 blob,
+    z = hash_to_bls_field([5;32])), rejects y + 1 and a swapped G2 argument, and agrees with the
+    scalar path on every case."""
+    o, s = pyoracle
+    case = [c for c in golden["cases"] if c["name"] == "C3_mod64"][0]
+    pr = [p for p in case["proofs"] if p["label"] == "fs5"][0]
+    C, PI = o.g1_decompress(bytes.fromhex(case["commitment"])), o.g1_decompress(bytes.fromhex(pr["proof"]))
+    z, y = int(pr["z"], 16), int(pr["y"], 16)
+    G = o.g1_decompress(bytes.fromhex("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"))
+
+    def be192(q):
+        (x0, x1), (y0, y1) = q
+        return b"".join(v.to_bytes(48, "big") for v in (x0, x1, y0, y1))
+    for dy, g2a, g2b, want in ((0, s.g2[0], s.g2[1], 1), (1, s.g2[0], s.g2[1], 0), (0, s.g2[1], s.g2[0], 0)):
+        p1 = o.g1_add(o.g1_add(C, o.g1_neg(o.g1_mul(G, (y + dy) % R))), o.g1_mul(PI, z))
+        args = (o.g1_compress(p1), be192(g2a), o.g1_compress(o.g1_neg(PI)), be192(g2b))
+        assert L.fc_pairing_check2(*args) == want
+        assert L.fc_pairing_check2_lanes(*args) == want
+    # an infinity argument drops its pair: e(inf, Q) e(P, Q') == 1 only if P is infinity too
+    inf = b"\xc0" + bytes(47)
+    assert L.fc_pairing_check2_lanes(inf, be192(s.g2[0]), inf, be192(s.g2[1])) == 1
+    assert L.fc_pairing_check2_lanes(inf, be192(s.g2[0]), o.g1_compress(G), be192(s.g2[1])) == 0
