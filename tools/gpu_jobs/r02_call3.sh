@@ -13,3 +13,5 @@ RAIKO_KZG_TRACE=1 python tests/tools/e2e_trace.py 8192 3 > gpurun_out/r02_c3_tra
 tail -5 gpurun_out/r02_c3_trace_8192.txt
 python bench.py --batch 9472 --steps 2 --warmup 2 --cpu-sample 16 > gpurun_out/r02_c3_bench_9472.json 2> gpurun_out/r02_c3_bench_9472.err
 echo "bench rc=$?"
+./tools/ubench/fpmul_dfma > gpurun_out/r02_c3_fpmul_dfma.txt 2>&1
+tail -8 gpurun_out/r02_c3_fpmul_dfma.txt
