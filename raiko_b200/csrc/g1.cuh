@@ -38,31 +38,11 @@ RK_HD void g1_from_affine(G1Xyzz& r, const G1Affine& p) {
     fe_const<FpTag, FP_ONE>(r.zz); fe_const<FpTag, FP_ONE>(r.zzz);
 }
 
-// r = 2 * (x, y, zz, zzz); works for affine input with zz = zzz = 1 too.
-RK_HD void g1_dbl(G1Xyzz& r, const G1Xyzz& a) {
-    if (g1_is_inf(a)) { g1_set_inf(r); return; }
-    Fp U, V, Wv, S, M, t, X3;
-    fe_dbl(U, a.y);                 // < 12p
-    fe_sqr(V, U);                   // < 1.3p
-    fe_mul(Wv, U, V);
-    fe_mul(S, a.x, V);
-    fe_sqr(t, a.x);
-    fe_add(M, t, t); fe_add(M, M, t);      // 3 X^2 < 3.4p
-    fe_sqr(X3, M);
-    fe_add(t, S, S);                        // 2S < 2.1p
-    fe_sub<FpTag, 4>(X3, X3, t);            // < 5.1p
-    fe_sub<FpTag, 6>(t, S, X3);             // < 7.1p
-    fe_mul(t, M, t);
-    fe_mul(U, Wv, a.y);                     // W*Y1 < 1.1p
-    fe_mul(r.zz, V, a.zz);
-    fe_mul(r.zzz, Wv, a.zzz);
-    fe_sub<FpTag, 2>(r.y, t, U);
-    fe_set(r.x, X3);
-}
-
-// Out-of-line Fp product / square for the MSM hot loop.  Inlined, one mixed addition is ~85 KB
-// of straight-line code (10 products), far beyond the instruction cache; called, the loop body
-// is ~15 KB.  The CUDA ABI keeps both 13-word operands and the result in registers (checked:
+// Out-of-line Fp product / square.  Inlined, one mixed addition is ~85 KB of straight-line code
+// (10 products), far beyond the instruction cache; called, a loop body is ~15 KB.  The MSM kernels
+// inline (their warps run in lockstep and share instruction fetches); the latency-bound
+// verification kernels (one or two warps per SM walking 255-bit scalars) call: template
+// parameter CALLS of the point operations below.  The CUDA ABI keeps both 13-word operands and the result in registers (checked:
 // no local-memory traffic, tools/ubench/noinline_test.cu), and the call costs ~3 %.
 #ifdef __CUDACC__
 static __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) { Fp r; fe_mul(r, a, b); return r; }
@@ -83,6 +63,29 @@ RK_HD void fp_sqr_sel(Fp& r, const Fp& a) {
     fe_sqr(r, a);
 }
 
+// r = 2 * (x, y, zz, zzz); works for affine input with zz = zzz = 1 too.
+template <bool CALLS = false>
+RK_HD void g1_dbl(G1Xyzz& r, const G1Xyzz& a) {
+    if (g1_is_inf(a)) { g1_set_inf(r); return; }
+    Fp U, V, Wv, S, M, t, X3;
+    fe_dbl(U, a.y);                 // < 12p
+    fp_sqr_sel<CALLS>(V, U);                   // < 1.3p
+    fp_mul_sel<CALLS>(Wv, U, V);
+    fp_mul_sel<CALLS>(S, a.x, V);
+    fp_sqr_sel<CALLS>(t, a.x);
+    fe_add(M, t, t); fe_add(M, M, t);      // 3 X^2 < 3.4p
+    fp_sqr_sel<CALLS>(X3, M);
+    fe_add(t, S, S);                        // 2S < 2.1p
+    fe_sub<FpTag, 4>(X3, X3, t);            // < 5.1p
+    fe_sub<FpTag, 6>(t, S, X3);             // < 7.1p
+    fp_mul_sel<CALLS>(t, M, t);
+    fp_mul_sel<CALLS>(U, Wv, a.y);                     // W*Y1 < 1.1p
+    fp_mul_sel<CALLS>(r.zz, V, a.zz);
+    fp_mul_sel<CALLS>(r.zzz, Wv, a.zzz);
+    fe_sub<FpTag, 2>(r.y, t, U);
+    fe_set(r.x, X3);
+}
+
 // acc += (x2, y2) affine (never infinity).
 template <bool CALLS = false>
 RK_HD void g1_madd(G1Xyzz& acc, const Fp& x2, const Fp& y2) {
@@ -101,7 +104,7 @@ RK_HD void g1_madd(G1Xyzz& acc, const Fp& x2, const Fp& y2) {
             G1Xyzz d;
             fe_set(d.x, x2); fe_set(d.y, y2);
             fe_const<FpTag, FP_ONE>(d.zz); fe_const<FpTag, FP_ONE>(d.zzz);
-            g1_dbl(acc, d);
+            g1_dbl<CALLS>(acc, d);
         } else {
             g1_set_inf(acc);
         }
@@ -123,40 +126,41 @@ RK_HD void g1_madd(G1Xyzz& acc, const Fp& x2, const Fp& y2) {
 }
 
 // a += b (both XYZZ)
+template <bool CALLS = false>
 RK_HD void g1_add(G1Xyzz& a, const G1Xyzz& b) {
     if (g1_is_inf(b)) return;
     if (g1_is_inf(a)) { a = b; return; }
     Fp U1, S1, P, Rr, PP, PPP, Q, t;
-    fe_mul(U1, a.x, b.zz);
-    fe_mul(P, b.x, a.zz);
-    fe_mul(S1, a.y, b.zzz);
-    fe_mul(Rr, b.y, a.zzz);
+    fp_mul_sel<CALLS>(U1, a.x, b.zz);
+    fp_mul_sel<CALLS>(P, b.x, a.zz);
+    fp_mul_sel<CALLS>(S1, a.y, b.zzz);
+    fp_mul_sel<CALLS>(Rr, b.y, a.zzz);
     fe_sub<FpTag, 2>(P, P, U1);             // < 3.1p
     fe_sub<FpTag, 2>(Rr, Rr, S1);
     if (fe_is_zero_mod(P)) {
         if (fe_is_zero_mod(Rr)) {
             G1Xyzz d = a;
-            g1_dbl(a, d);
+            g1_dbl<CALLS>(a, d);
         } else {
             g1_set_inf(a);
         }
         return;
     }
-    fe_sqr(PP, P);
-    fe_mul(PPP, P, PP);
-    fe_mul(Q, U1, PP);
-    fe_sqr(a.x, Rr);
+    fp_sqr_sel<CALLS>(PP, P);
+    fp_mul_sel<CALLS>(PPP, P, PP);
+    fp_mul_sel<CALLS>(Q, U1, PP);
+    fp_sqr_sel<CALLS>(a.x, Rr);
     fe_add(t, Q, Q);
     fe_add(t, t, PPP);
     fe_sub<FpTag, 4>(a.x, a.x, t);
     fe_sub<FpTag, 6>(t, Q, a.x);
-    fe_mul(t, Rr, t);
-    fe_mul(Q, S1, PPP);
+    fp_mul_sel<CALLS>(t, Rr, t);
+    fp_mul_sel<CALLS>(Q, S1, PPP);
     fe_sub<FpTag, 2>(a.y, t, Q);
-    fe_mul(a.zz, a.zz, b.zz);
-    fe_mul(a.zz, a.zz, PP);
-    fe_mul(a.zzz, a.zzz, b.zzz);
-    fe_mul(a.zzz, a.zzz, PPP);
+    fp_mul_sel<CALLS>(a.zz, a.zz, b.zz);
+    fp_mul_sel<CALLS>(a.zz, a.zz, PP);
+    fp_mul_sel<CALLS>(a.zzz, a.zzz, b.zzz);
+    fp_mul_sel<CALLS>(a.zzz, a.zzz, PPP);
 }
 
 // XYZZ -> affine Montgomery coordinates (< 1.1p); returns false for infinity.
@@ -194,12 +198,46 @@ RK_HD_NOINLINE void g1_scalar_mul(G1Xyzz& r, const G1Affine& p, const uint32_t* 
     g1_set_inf(acc);
     for (int bit = 255; bit >= 0; bit--) {
         G1Xyzz t;
-        g1_dbl(t, acc);
+        g1_dbl<true>(t, acc);
         acc = t;
-        if ((k[bit >> 5] >> (bit & 31)) & 1) g1_madd(acc, p.x, p.y);
+        if ((k[bit >> 5] >> (bit & 31)) & 1) g1_madd<true>(acc, p.x, p.y);
     }
     r = acc;
 }
+// Membership of an affine curve point in the prime-order subgroup G1, by the endomorphism test
+// (M. Scott, "A note on group membership tests for G1, G2 and GT on BLS pairing-friendly curves",
+// ePrint 2021/1130): with u the BLS parameter (|u| = 0xd201000000010000) and r = u^4 - u^2 + 1,
+// -u^2 is a cube root of unity mod r and acts on G1 as phi(x, y) = (BETA x, y); the paper proves
+// that for BLS12-381   P in G1  <=>  [u^2] P = -phi(P) = (BETA x, -y).   Two 64-bit
+// double-and-add passes (126 doublings + 10 additions) instead of a 255-bit multiplication by r:
+// a third of the work.  The host tests check it against [r]P == infinity on points of G1, on random
+// curve points and on points of every small prime order dividing the cofactor.
+RK_HD_NOINLINE bool g1_in_subgroup(const G1Affine& p) {
+    const uint64_t e = ((uint64_t)BLS_X_ABS_W32::at(1) << 32) | BLS_X_ABS_W32::at(0);
+    G1Xyzz t, acc;
+    g1_from_affine(acc, p);                           // [|u|] P, affine base
+    for (int bit = 62; bit >= 0; bit--) {
+        g1_dbl<true>(t, acc); acc = t;
+        if ((e >> bit) & 1) g1_madd<true>(acc, p.x, p.y);
+    }
+    const G1Xyzz base = acc;                          // [|u|] ([|u|] P), projective base
+    for (int bit = 62; bit >= 0; bit--) {
+        g1_dbl<true>(t, acc); acc = t;
+        if ((e >> bit) & 1) g1_add<true>(acc, base);
+    }
+    if (g1_is_inf(acc)) return false;                 // P is never infinity here
+    // acc == (BETA x, -y) ?   X = BETA x ZZ,  Y = -y ZZZ
+    Fp beta, bx, lhs, d;
+    fe_const<FpTag, FP_BETA>(beta);
+    fe_mul(bx, beta, p.x);
+    fe_mul(lhs, bx, acc.zz);
+    fe_sub<FpTag, 6>(d, lhs, acc.x);
+    if (!fe_is_zero_mod(d)) return false;
+    fe_mul(lhs, p.y, acc.zzz);
+    fe_add(d, lhs, acc.y);                            // y ZZZ + Y == 0 ?
+    return fe_is_zero_mod(d);
+}
+
 // XYZZ -> affine (one Fermat inversion).  Returns false for infinity.
 RK_HD bool g1_xyzz_to_affine(G1Affine& r, const G1Xyzz& a) {
     if (g1_is_inf(a)) return false;

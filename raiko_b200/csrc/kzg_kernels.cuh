@@ -1341,11 +1341,7 @@ __global__ void __launch_bounds__(64) k_g1_decompress_validate(const uint8_t* in
     int rc = g1_decompress(a, in + 48 * (size_t)i);
     if (rc < 0) { atomicCAS(err, 0, i + 1); out_inf[i] = 1; return; }
     if (rc == 1) { out_inf[i] = 1; return; }
-    uint32_t k[8];
-    for (int w = 0; w < 8; w++) k[w] = FR_MOD_W32::at(w);
-    G1Xyzz t;
-    g1_scalar_mul(t, a, k);
-    if (!g1_is_inf(t)) { atomicCAS(err, 0, i + 1); out_inf[i] = 1; return; }
+    if (!g1_in_subgroup(a)) { atomicCAS(err, 0, i + 1); out_inf[i] = 1; return; }   // endomorphism test, g1.cuh
     out[i] = a;
     out_inf[i] = 0;
 }

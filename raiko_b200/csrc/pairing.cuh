@@ -405,46 +405,49 @@ constexpr int PAIRING_STEPS = 68;                  // 63 doublings + 5 additions
 struct LineStep { Fp l0, l6, a, b; };              // line = l0 + l6 w^6 + (a xP) w^2 + (b xP) w^8 + yP w^3
 
 // lane k: raw coefficients t[k] (lo) and t[k + 12] (hi) of a * b
-RK_HD void fp12_mul_lane(int k, const Fp* a, const Fp* b, Fp& lo, Fp& hi) {
+RK_HD_NOINLINE void fp12_mul_lane(int k, const Fp* a, const Fp* b, Fp& lo, Fp& hi) {
     fe_zero(lo); fe_zero(hi);
+#pragma unroll 1
     for (int i = 0; i < 12; i++) {
         Fp m;
-        if (i <= k) { fe_mul(m, a[i], b[k - i]); fq_add(lo, lo, m); }
-        else { fe_mul(m, a[i], b[k + 12 - i]); fq_add(hi, hi, m); }
+        if (i <= k) { fp_mul_sel<true>(m, a[i], b[k - i]); fq_add(lo, lo, m); }
+        else { fp_mul_sel<true>(m, a[i], b[k + 12 - i]); fq_add(hi, hi, m); }
     }
 }
 // lane k: the same for a * a, cross terms once and doubled (7 products)
-RK_HD void fp12_sqr_lane(int k, const Fp* a, Fp& lo, Fp& hi) {
+RK_HD_NOINLINE void fp12_sqr_lane(int k, const Fp* a, Fp& lo, Fp& hi) {
     fe_zero(lo); fe_zero(hi);
     for (int pass = 0; pass < 2; pass++) {
         const int n = pass == 0 ? k : k + 12;
         Fp& t = pass == 0 ? lo : hi;
         const int i0 = n > 11 ? n - 11 : 0;
+#pragma unroll 1
         for (int i = i0; 2 * i <= n; i++) {
             const int j = n - i;
             Fp m;
-            if (i == j) fe_sqr(m, a[i]);
-            else { fe_mul(m, a[i], a[j]); fq_dbl(m, m); }
+            if (i == j) fp_sqr_sel<true>(m, a[i]);
+            else { fp_mul_sel<true>(m, a[i], a[j]); fq_dbl(m, m); }
             fq_add(t, t, m);
         }
     }
 }
 // lane k: the same for a * (l0 + l2 w^2 + l3 w^3 + l6 w^6 + l8 w^8) (5 products)
-RK_HD void fp12_line_lane(int k, const Fp* a, const LineCoeffs& l, Fp& lo, Fp& hi) {
+RK_HD_NOINLINE void fp12_line_lane(int k, const Fp* a, const LineCoeffs& l, Fp& lo, Fp& hi) {
     fe_zero(lo); fe_zero(hi);
     const int es[5] = {0, 2, 3, 6, 8};
+#pragma unroll 1
     for (int q = 0; q < 5; q++) {
         const int e = es[q];
         const Fp& c = e == 0 ? l.l0 : e == 2 ? l.l2 : e == 3 ? l.l3 : e == 6 ? l.l6 : l.l8;
         Fp m;
-        if (e <= k) { fe_mul(m, a[k - e], c); fq_add(lo, lo, m); }
-        else { fe_mul(m, a[k + 12 - e], c); fq_add(hi, hi, m); }
+        if (e <= k) { fp_mul_sel<true>(m, a[k - e], c); fq_add(lo, lo, m); }
+        else { fp_mul_sel<true>(m, a[k + 12 - e], c); fq_add(hi, hi, m); }
     }
 }
 // lane k: coefficient k after folding t[0..22] (t[23] ignored) modulo w^12 = 2 w^6 - 2.
 //   w^(12+j) = 2 w^(6+j) - 2 w^j            (j <= 5)
 //   w^(12+j) = 2 w^j - 4 w^(j-6)            (6 <= j <= 10)
-RK_HD void fp12_fold_lane(int k, const Fp* t, Fp& out) {
+RK_HD_NOINLINE void fp12_fold_lane(int k, const Fp* t, Fp& out) {
     Fp r = t[k], d;
     if (k <= 5) {
         fq_dbl(d, t[12 + k]); fq_sub(r, r, d);                         // - 2 T_k
@@ -457,15 +460,16 @@ RK_HD void fp12_fold_lane(int k, const Fp* t, Fp& out) {
 }
 // lane k: coefficient k of a^(p^e) (TAB = FP12_FROB1 / FP12_FROB2): two products
 template <class TAB>
-RK_HD void fp12_frob_lane(int k, const Fp* a, Fp& out) {
+RK_HD_NOINLINE void fp12_frob_lane(int k, const Fp* a, Fp& out) {
     const int half = k >= 6 ? 13 : 0;
     Fp acc;
     fe_zero(acc);
+#pragma unroll 1
     for (int q = 0; q < 2; q++) {
         const int j = (k % 6) + 6 * q;
         Fp c, m;
         for (int l = 0; l < FP_N; l++) c.v[l] = frob_word<TAB>(j * 26 + half + l);
-        fe_mul(m, a[j], c);
+        fp_mul_sel<true>(m, a[j], c);
         fq_add(acc, acc, m);
     }
     out = acc;
@@ -520,7 +524,7 @@ template <class X>
 struct LaneFp12 {
     Fp c[X::LANES];
 };
-template <class X> RK_HD void lp_mul(X& x, LaneFp12<X>& r, const LaneFp12<X>& a, const LaneFp12<X>& b) {
+template <class X> RK_HD_NOINLINE void lp_mul(X& x, LaneFp12<X>& r, const LaneFp12<X>& a, const LaneFp12<X>& b) {
     for (int i = 0; i < X::LANES; i++) { x.publish(0, x.lane(i), a.c[i]); x.publish(1, x.lane(i), b.c[i]); }
     x.sync();
     for (int i = 0; i < X::LANES; i++) { Fp lo, hi; fp12_mul_lane(x.lane(i), x.read(0), x.read(1), lo, hi); x.publish(2, x.lane(i), lo); x.publish(3, x.lane(i), hi); }
@@ -528,7 +532,7 @@ template <class X> RK_HD void lp_mul(X& x, LaneFp12<X>& r, const LaneFp12<X>& a,
     for (int i = 0; i < X::LANES; i++) fp12_fold_lane(x.lane(i), x.read(2), r.c[i]);
     x.sync();
 }
-template <class X> RK_HD void lp_sqr(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
+template <class X> RK_HD_NOINLINE void lp_sqr(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
     for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
     x.sync();
     for (int i = 0; i < X::LANES; i++) { Fp lo, hi; fp12_sqr_lane(x.lane(i), x.read(0), lo, hi); x.publish(2, x.lane(i), lo); x.publish(3, x.lane(i), hi); }
@@ -536,7 +540,7 @@ template <class X> RK_HD void lp_sqr(X& x, LaneFp12<X>& r, const LaneFp12<X>& a)
     for (int i = 0; i < X::LANES; i++) fp12_fold_lane(x.lane(i), x.read(2), r.c[i]);
     x.sync();
 }
-template <class X> RK_HD void lp_line(X& x, LaneFp12<X>& r, const LaneFp12<X>& a, const LineCoeffs& l) {
+template <class X> RK_HD_NOINLINE void lp_line(X& x, LaneFp12<X>& r, const LaneFp12<X>& a, const LineCoeffs& l) {
     for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
     x.sync();
     for (int i = 0; i < X::LANES; i++) { Fp lo, hi; fp12_line_lane(x.lane(i), x.read(0), l, lo, hi); x.publish(2, x.lane(i), lo); x.publish(3, x.lane(i), hi); }
@@ -544,7 +548,7 @@ template <class X> RK_HD void lp_line(X& x, LaneFp12<X>& r, const LaneFp12<X>& a
     for (int i = 0; i < X::LANES; i++) fp12_fold_lane(x.lane(i), x.read(2), r.c[i]);
     x.sync();
 }
-template <class TAB, class X> RK_HD void lp_frob(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
+template <class TAB, class X> RK_HD_NOINLINE void lp_frob(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
     for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
     x.sync();
     for (int i = 0; i < X::LANES; i++) fp12_frob_lane<TAB>(x.lane(i), x.read(0), r.c[i]);
@@ -553,7 +557,7 @@ template <class TAB, class X> RK_HD void lp_frob(X& x, LaneFp12<X>& r, const Lan
 template <class X> RK_HD void lp_conj(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
     for (int i = 0; i < X::LANES; i++) { if (x.lane(i) & 1) fq_neg(r.c[i], a.c[i]); else r.c[i] = a.c[i]; }
 }
-template <class X> RK_HD void lp_pow_x(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
+template <class X> RK_HD_NOINLINE void lp_pow_x(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
     LaneFp12<X> acc = a;
     const uint64_t e = ((uint64_t)BLS_X_ABS_W32::at(1) << 32) | BLS_X_ABS_W32::at(0);
     for (int bit = 62; bit >= 0; bit--) {
@@ -566,7 +570,7 @@ template <class X> RK_HD void lp_pow_x(X& x, LaneFp12<X>& r, const LaneFp12<X>& 
 // lies in Fp2 = {x + y w^6}; its inverse is ((x + 2y) - y w^6) / (x^2 + 2xy + 2y^2) because the
 // conjugate of w^6 = 1 + i is 2 - w^6.  1/a = a^q * N6^(p^2) * N6^(p^4) / N2.  One Fp inversion.
 // Returns false when a = 0.
-template <class X> RK_HD bool lp_inv(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
+template <class X> RK_HD_NOINLINE bool lp_inv(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
     LaneFp12<X> aq, n6, f2, f4, m, n2;
     lp_conj(x, aq, a);
     lp_mul(x, n6, a, aq);

@@ -168,4 +168,20 @@ int fc_pairing_check2_lanes(const uint8_t* p1, const uint8_t* q1, const uint8_t*
     HostLanes x;
     return lane_pairing_product_is_one(x, ps, inf, l0, l1) ? 1 : 0;
 }
+// subgroup membership of an affine point given as 96 bytes (x | y big-endian canonical), which need
+// not be in G1: 1 / 0 by the endomorphism test, and by [r]P == infinity; -1 when not on the curve
+static int load_xy(G1Affine& a, const uint8_t* xy) {
+    fp_from_be48_mont(a.x, xy); fp_from_be48_mont(a.y, xy + 48);
+    Fp l, r3, b4, t;
+    fe_sqr(l, a.y); fe_sqr(r3, a.x); fe_mul(r3, r3, a.x);
+    fe_const<FpTag, FP_B_COEFF>(b4); fe_add(r3, r3, b4);
+    fe_sub<FpTag, 4>(t, l, r3);
+    return fe_is_zero_mod(t) ? 0 : -1;
+}
+int fc_g1_in_subgroup_fast(const uint8_t* xy) { G1Affine a; if (load_xy(a, xy)) return -1; return g1_in_subgroup(a) ? 1 : 0; }
+int fc_g1_in_subgroup_slow(const uint8_t* xy) {
+    G1Affine a; if (load_xy(a, xy)) return -1;
+    uint32_t k[8]; for (int w = 0; w < 8; w++) k[w] = FR_MOD_W32::at(w);
+    G1Xyzz t; g1_scalar_mul(t, a, k); return g1_is_inf(t) ? 1 : 0;
+}
 }

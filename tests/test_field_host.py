@@ -211,3 +211,39 @@ def test_lane_parallel_pairing_check(L, pyoracle, golden):
     inf = b"\xc0" + bytes(47)
     assert L.fc_pairing_check2_lanes(inf, be192(s.g2[0]), inf, be192(s.g2[1])) == 1
     assert L.fc_pairing_check2_lanes(inf, be192(s.g2[0]), o.g1_compress(G), be192(s.g2[1])) == 0
+
+
+def test_g1_subgroup_check_by_endomorphism(L, pyoracle):
+    """g1_in_subgroup ([u^2]P == (BETA x, -y), Scott ePrint 2021/1130) against [r]P == infinity:
+    points of G1, random curve points, and points whose order is (or contains) each small prime
+    dividing the cofactor 3 * 11^2 * 10177^2 * 859267^2 * 52437899^2 -- the cases a sloppy
+    membership test lets through."""
+    o, _ = pyoracle
+    rnd = random.Random(7)
+    u = 0xD201000000010000
+    cof = (u + 1) ** 2 // 3
+    assert R == u ** 4 - u ** 2 + 1
+    G = o.g1_decompress(bytes.fromhex("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"))
+
+    def curve_point():
+        while True:
+            x = rnd.randrange(P)
+            y = o.fp_sqrt((x * x * x + 4) % P)
+            if y is not None and (y * y - x * x * x - 4) % P == 0:
+                return (x, y)
+
+    def xy(pt):
+        return pt[0].to_bytes(48, "big") + pt[1].to_bytes(48, "big")
+    assert o.g1_mul_raw(curve_point(), cof * R) is None               # the curve order
+    cases = [(o.g1_mul(G, k), 1) for k in (1, 2, rnd.randrange(R), R - 1)] + [(curve_point(), 0) for _ in range(10)]
+    for l, e in ((3, 1), (11, 2), (10177, 2), (859267, 2), (52437899, 2)):
+        while True:
+            q = o.g1_mul_raw(curve_point(), cof * R // l ** e)        # the l-primary part has exponent l
+            if q is not None:
+                break
+        assert o.g1_mul_raw(q, l) is None
+        cases += [(q, 0), (o.g1_add(q, o.g1_mul(G, rnd.randrange(1, R))), 0)]
+    for pt, want in cases:
+        assert L.fc_g1_in_subgroup_slow(xy(pt)) == want
+        assert L.fc_g1_in_subgroup_fast(xy(pt)) == want
+    assert L.fc_g1_in_subgroup_fast(xy((1, 1))) == -1                 # not on the curve
