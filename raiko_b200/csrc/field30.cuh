@@ -117,9 +117,48 @@ using Fp = Fe<FpTag>;
 using Fr = Fe<FrTag>;
 
 // ---------------------------------------------------------------------------
-// Montgomery reduction of 2N-1 product columns (shared by mul and sqr)
-//   c[k] < 2^63.71 on entry (at most N products of two 30-bit limbs).
+// Montgomery product.  RK_MUL_FORM selects the formulation (all give the same integer result,
+// (a b + M mod) / R with M fixed by a b mod R; host-checked in tests/test_field_host.py):
+//   0  operand scanning into 2N 64-bit columns, then N reduction rows; the columns that would
+//      exceed 64 bits are split at 30 bits first (round 1).
+//   1  the same, but the split is at bit 32: the high WORD of a hot column moves up one column
+//      (x4), which costs two instructions per column instead of five.
+//   2  row-interleaved: product row i is followed at once by reduction row i and the window of
+//      N+1 live columns slides down one limb, so the product needs 28 accumulator registers
+//      instead of 52; one split pass (at bit 32) in the middle keeps every column below 2^64.
 // ---------------------------------------------------------------------------
+#ifndef RK_MUL_FORM
+#define RK_MUL_FORM 0
+#endif
+
+// lo + 4 * up as one multiply-add (IMAD.WIDE with an immediate multiplicand is full rate; stated as a
+// shift, the compiler spends five ALU instructions on the two words).
+RK_HD uint64_t mad4(uint64_t lo, uint32_t up) {
+#ifdef __CUDA_ARCH__
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(up), "l"(lo));
+    return r;
+#else
+    return lo + ((uint64_t)up << 2);
+#endif
+}
+
+// Carry-save split of columns c[lo..hi] at bit 32: column k keeps its low word and receives four
+// times the high word of column k-1 (2^32 = 4 * 2^30); c[hi+1] receives the last one.  No ripple.
+template <int LO, int HI, int LEN>
+RK_HD void split_columns32(uint64_t (&c)[LEN]) {
+    uint32_t up = 0;
+#pragma unroll
+    for (int k = LO; k <= HI; k++) {
+        const uint32_t hi = (uint32_t)(c[k] >> 32);
+        c[k] = mad4((uint32_t)c[k], up);
+        up = hi;
+    }
+    c[HI + 1] = mad4(c[HI + 1], up);
+}
+
+// Montgomery reduction of 2N-1 product columns (shared by mul and sqr, forms 0 and 1)
+//   c[k] < 2^63.71 on entry (at most N products of two 30-bit limbs).
 template <class F>
 RK_HD void mont_reduce_columns(Fe<F>& r, uint64_t (&c)[2 * F::N]) {
     constexpr int N = F::N;
@@ -128,6 +167,9 @@ RK_HD void mont_reduce_columns(Fe<F>& r, uint64_t (&c)[2 * F::N]) {
     // columns first (carry-save: no ripple, every step independent).
     constexpr int HOT_LO = 7, HOT_HI = 2 * N - 2 - 7;
     if (HOT_LO <= HOT_HI) {
+#if RK_MUL_FORM == 1
+        split_columns32<HOT_LO, HOT_HI, 2 * N>(c);
+#else
         uint64_t carry_in = 0;
 #pragma unroll
         for (int k = HOT_LO; k <= HOT_HI; k++) {
@@ -136,6 +178,7 @@ RK_HD void mont_reduce_columns(Fe<F>& r, uint64_t (&c)[2 * F::N]) {
             carry_in = hi;
         }
         c[HOT_HI + 1] += carry_in;
+#endif
     }
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -153,9 +196,49 @@ RK_HD void mont_reduce_columns(Fe<F>& r, uint64_t (&c)[2 * F::N]) {
     r.v[N - 1] = launder((uint32_t)c[2 * N - 1]);
 }
 
+// Form 2 building blocks.  The window c[0..N] holds weights i .. i+N during row i.
+template <class F>
+RK_HD void mont_window_step(uint64_t (&c)[F::N + 1]) {
+    constexpr int N = F::N;
+    uint32_t m = launder(((uint32_t)c[0] * F::PINV) & LIMB_MASK);
+#pragma unroll
+    for (int j = 0; j < N; j++) mac_const(c[j], m, F::MOD::at(j));
+    c[1] += c[0] >> LIMB_BITS;           // low 30 bits of c[0] are zero now
+#pragma unroll
+    for (int j = 0; j < N; j++) c[j] = c[j + 1];
+    c[N] = 0;
+}
+template <class F>
+RK_HD void mont_window_finish(Fe<F>& r, uint64_t (&c)[F::N + 1]) {
+    constexpr int N = F::N;
+#pragma unroll
+    for (int k = 0; k < N - 1; k++) {
+        c[k + 1] += c[k] >> LIMB_BITS;
+        r.v[k] = launder((uint32_t)c[k] & LIMB_MASK);
+    }
+    r.v[N - 1] = launder((uint32_t)c[N - 1]);      // c[N] is zero: the result is below 2^(30 N)
+}
+
 template <class F>
 RK_HD void fe_mul(Fe<F>& r, const Fe<F>& a, const Fe<F>& b) {
     constexpr int N = F::N;
+#if RK_MUL_FORM == 2
+    // Every row adds one product and one reduction product (< 2^60 each) to a column, and a
+    // column lives for at most N rows: split once after row 6 (14 terms), the remaining
+    // N - 7 <= 6 rows add at most 12 more.
+    static_assert(N <= 13, "one split pass covers at most 13 rows");
+    uint64_t c[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; k++) c[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+#pragma unroll
+        for (int j = 0; j < N; j++) mac(c[j], a.v[i], b.v[j]);
+        mont_window_step<F>(c);
+        if (i == 6 && N > 7) split_columns32<0, N - 1, N + 1>(c);
+    }
+    mont_window_finish<F>(r, c);
+#else
     uint64_t c[2 * N];
 #pragma unroll
     for (int k = 0; k < 2 * N; k++) c[k] = 0;
@@ -164,17 +247,36 @@ RK_HD void fe_mul(Fe<F>& r, const Fe<F>& a, const Fe<F>& b) {
 #pragma unroll
         for (int j = 0; j < N; j++) mac(c[i + j], a.v[i], b.v[j]);
     mont_reduce_columns<F>(r, c);
+#endif
 }
 
 template <class F>
 RK_HD void fe_sqr(Fe<F>& r, const Fe<F>& a) {
     constexpr int N = F::N;
-    uint64_t c[2 * N];
     uint32_t a2[N];
 #pragma unroll
-    for (int k = 0; k < 2 * N; k++) c[k] = 0;
-#pragma unroll
     for (int i = 0; i < N; i++) a2[i] = launder(a.v[i] << 1);
+#if RK_MUL_FORM == 2
+    // Row i adds a_i^2 (weight 2i) and the doubled products 2 a_i a_j, j > i: a column gathers its
+    // product weight earlier than in the general product (up to 2 units of 2^60 per row from
+    // products plus one from the reduction), so the window is split after rows 3 and 7.
+    static_assert(N <= 13, "split schedule below is for at most 13 rows");
+    uint64_t c[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; k++) c[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        mac(c[i], a.v[i], a.v[i]);
+#pragma unroll
+        for (int j = i + 1; j < N; j++) mac(c[j], a2[i], a.v[j]);
+        mont_window_step<F>(c);
+        if ((i == 3 || i == 7) && i < N - 1) split_columns32<0, N - 1, N + 1>(c);
+    }
+    mont_window_finish<F>(r, c);
+#else
+    uint64_t c[2 * N];
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) c[k] = 0;
 #pragma unroll
     for (int i = 0; i < N; i++) {
         mac(c[2 * i], a.v[i], a.v[i]);
@@ -182,6 +284,7 @@ RK_HD void fe_sqr(Fe<F>& r, const Fe<F>& a) {
         for (int j = i + 1; j < N; j++) mac(c[i + j], a2[i], a.v[j]);
     }
     mont_reduce_columns<F>(r, c);
+#endif
 }
 
 // r = a + b, normalised.  No modular reduction: the caller tracks the bound.
@@ -217,6 +320,68 @@ RK_HD void fe_neg(Fe<F>& r, const Fe<F>& a) {
         int32_t t = (int32_t)F::modx(K, i) - (int32_t)a.v[i] + carry;
         carry = t >> LIMB_BITS;
         r.v[i] = launder((uint32_t)t & LIMB_MASK);
+    }
+}
+
+// r = a + b limb by limb, NOT normalised (limbs < 2^31).  Only for a value whose sole use is as the
+// subtrahend of fe_sub / fe_sub_reduce below, whose carry pass absorbs the wide limbs.
+template <class F>
+RK_HD void fe_add_raw(Fe<F>& r, const Fe<F>& a, const Fe<F>& b) {
+#pragma unroll
+    for (int i = 0; i < F::N; i++) r.v[i] = a.v[i] + b.v[i];
+}
+
+// r = (neg ? -a : a) - b + K*mod in one carry pass (neg is per thread: no divergence).  The caller
+// guarantees a + b <= K*mod.  b may be a raw sum (limbs < 2^31).
+template <class F, int K>
+RK_HD void fe_sub_cneg(Fe<F>& r, const Fe<F>& a, const Fe<F>& b, bool neg) {
+    const uint32_t sb = neg ? 1u : 0u, sm = 0u - sb;
+    int32_t carry = (int32_t)sb;                 // -a = ~a + 1 limb by limb: the +1 enters once, at limb 0 ...
+    const uint32_t fix = sm & LIMB_MASK;         // ... and ~a_i = (a_i ^ mask30) - 2^30 + 2^30 per limb, see below
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+        // neg: (a_i ^ 0x3fffffff) = 2^30 - 1 - a_i, so sum_i (2^30-1-a_i) 2^(30 i) + 1 = 2^(30 N) - a: the
+        // 2^(30 N) leaves through the discarded carry out of the top limb (computed modulo 2^(30 N)).
+        int32_t t = (int32_t)((a.v[i] ^ fix) + F::modx(K, i)) - (int32_t)b.v[i] + carry;
+        carry = t >> LIMB_BITS;
+        r.v[i] = launder((uint32_t)t & LIMB_MASK);
+    }
+}
+
+// Multiples 0..8 of the modulus as normalised limbs, row-major [9][N]: the table fe_sub_reduce reads
+// (kernels keep it in shared memory; fe_fill_multiples writes it).
+template <class F>
+RK_HD void fe_fill_multiples(uint32_t* tab) {
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+        tab[i] = 0;
+        tab[1 * F::N + i] = F::modx(1, i); tab[2 * F::N + i] = F::modx(2, i); tab[3 * F::N + i] = F::modx(3, i);
+        tab[4 * F::N + i] = F::modx(4, i); tab[5 * F::N + i] = F::modx(5, i); tab[6 * F::N + i] = F::modx(6, i);
+        tab[7 * F::N + i] = F::modx(7, i); tab[8 * F::N + i] = F::modx(8, i);
+    }
+}
+
+// r = a - b + (K - q)*mod in ONE carry pass, q <= K estimated from the top limbs before the pass:
+// the subtraction and the loose reduction that used to follow it (fe_sub<K> + fe_reduce_loose, two
+// passes and a 64-bit multiply-subtract per limb).  a normalised, b normalised or a raw sum (limbs
+// < 2^31), b <= K*mod, K <= 8.  Result in [0, max(mod + 12 * 2^(30 (N-1)), a)): q never exceeds
+// value / mod, and it stops at K only when a - b itself is already that small.
+// tab = fe_fill_multiples' table.
+template <class F, int K>
+RK_HD void fe_sub_reduce(Fe<F>& r, const Fe<F>& a, const Fe<F>& b, const uint32_t* tab) {
+    constexpr int N = F::N;
+    // top limb of the unreduced result, not counting the carry into it (which is in [-2, 1])
+    const int32_t T = (int32_t)(a.v[N - 1] + F::modx(K, N - 1)) - (int32_t)b.v[N - 1];
+    uint32_t q = T < 2 ? 0u : (uint32_t)(T - 2) / (F::MOD::at(N - 1) + 1u);      // q*mod <= value
+    q = q > (uint32_t)K ? (uint32_t)K : q;
+    const uint32_t* row = tab + ((uint32_t)K - q) * N;
+    int32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        int32_t t = (int32_t)(a.v[i] + row[i]) - (int32_t)b.v[i] + carry;
+        carry = t >> LIMB_BITS;
+        if (i < N - 1) r.v[i] = launder((uint32_t)t & LIMB_MASK);
+        else r.v[i] = (uint32_t)t;
     }
 }
 

@@ -222,7 +222,24 @@ struct MsmAffParams {
 };
 constexpr int AFF_WORDS = 39;   // per chain and thread: x[13] y[13] prefix[13]
 constexpr int MSM_AFF_MAX_K = 64;
-constexpr int MSM_AFF_THREADS = 512;   // 16 warps per SM at 128 registers
+// Threads per CTA (one CTA per SM), register cap and lockstep groups of k_msm_affine.  Compile-time
+// so that A/B builds (-DRK_AFF_THREADS=640 -DRK_AFF_REGS=96 ...) need no source edits.
+#ifndef RK_AFF_THREADS
+#define RK_AFF_THREADS 512             // 16 warps per SM at 128 registers
+#endif
+#ifndef RK_AFF_REGS
+#define RK_AFF_REGS 128
+#endif
+#ifndef RK_AFF_SYNC
+#define RK_AFF_SYNC 2
+#endif
+// 1: fused limb passes in the backward loop (raw x1 + x2, conditional negation folded into the
+// subtraction, subtraction + loose reduction in one pass against a shared-memory table of multiples
+// of p); 0: one pass per operation, as in round 1.
+#ifndef RK_AFF_FUSE
+#define RK_AFF_FUSE 0
+#endif
+constexpr int MSM_AFF_THREADS = RK_AFF_THREADS;
 
 #ifdef RK_TU_MSM
 __device__ __forceinline__ void unpack_entry_x(Fp& x, const uint4 (&t)[3]) {
@@ -284,6 +301,11 @@ template <int THREADS, int SYNC>
 __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
     extern __shared__ uint32_t sh_code[];          // [K][THREADS]: table entry index + 1, bit 31 = negate; 0 = no entry
     const int tid = threadIdx.x, lane = tid & 31;
+#if RK_AFF_FUSE
+    __shared__ uint32_t sh_pmul[9 * FP_N];         // k * p, k = 0..8 (fe_sub_reduce)
+    if (tid == 0) fe_fill_multiples<FpTag>(sh_pmul);
+    __syncthreads();
+#endif
     const int K = prm.K;                           // even
     const int c = prm.g.c, W = prm.g.W;
     const uint32_t half = prm.g.half, cmask = (1u << c) - 1u;
@@ -437,6 +459,39 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
                     chain_load<THREADS>(r, cs, 0);
                     raw_to_fp(u, r);                       // x1 < 1.2p
                 }
+#if RK_AFF_FUSE
+                fe_sub<FpTag, 2>(lam, t, u);               // d_k
+                fe_mul(I, I, lam);
+                fe_add_raw(u, u, t);                       // x1 + x2 < 2.1p, limbs < 2^31: only ever subtracted
+                {
+                    uint4 ty[3];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) ty[q] = ldg_nc(ep + 3 + q);
+                    unpack_entry_x(t, ty);                 // y2 < p
+                    FpRaw r;
+                    chain_load<THREADS>(r, cs, 1);
+                    Fp y1;
+                    raw_to_fp(y1, r);                      // < 2p
+                    fe_sub_cneg<FpTag, 4>(t, t, y1, (code >> 31) != 0);   // +-y2 - y1 + 4p < 5p
+                }
+                fe_mul(lam, t, inv);
+                fe_sqr(t, lam);
+                fe_sub_reduce<FpTag, 3>(t, t, u, sh_pmul); // x3 < 1.01p
+                {
+                    FpRaw r;
+                    chain_load<THREADS>(r, cs, 0);
+                    raw_to_fp(u, r);                       // x1 again
+                }
+                chain_store<THREADS>(cs, 0, t);
+                fe_sub<FpTag, 2>(u, u, t);                 // x1 - x3 < 3.2p
+                fe_mul(u, lam, u);
+                {
+                    FpRaw r;
+                    chain_load<THREADS>(r, cs, 1);
+                    raw_to_fp(t, r);                       // y1 again
+                }
+                fe_sub_reduce<FpTag, 2>(u, u, t, sh_pmul); // y3 < 1.01p
+#else
                 fe_sub<FpTag, 2>(lam, t, u);               // d_k
                 fe_mul(I, I, lam);
                 fe_add(u, u, t);                           // x1 + x2 < 2.4p, kept for x3
@@ -471,6 +526,7 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
                 }
                 fe_sub<FpTag, 2>(u, u, t);                 // y3 < 3.2p
                 fe_reduce_loose<FpTag>(u);
+#endif
                 chain_store<THREADS>(cs, 1, u);
             }
         }
@@ -513,7 +569,7 @@ __device__ __forceinline__ void msm_affine_body(const MsmAffParams& prm) {
 // The kernel is latency-bound (two warps per scheduler left the multiply pipe 64 % busy), so
 // registers are spent on resident warps rather than load buffers, and the two lockstep groups
 // drift apart so one group's multiply phase overlaps the other's carry/ALU phase.
-__global__ void __maxnreg__(128) k_msm_affine(MsmAffParams prm) { msm_affine_body<MSM_AFF_THREADS, 2>(prm); }
+__global__ void __maxnreg__(RK_AFF_REGS) k_msm_affine(MsmAffParams prm) { msm_affine_body<MSM_AFF_THREADS, RK_AFF_SYNC>(prm); }
 #endif  // RK_TU_MSM (affine)
 
 #ifdef RK_TU_MSM

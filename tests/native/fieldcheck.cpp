@@ -68,6 +68,39 @@ int fc_g1_affine_batch_add(const uint8_t* accs, const uint8_t* pts, int n, uint8
         g1_compress_affine(out + 48 * k, A[k]);
     }
     return 0; }
+// the fused limb passes of k_msm_affine's backward loop (RK_AFF_FUSE)
+void fc_fp_sub_cneg4(const uint32_t* a, const uint32_t* b, int neg, uint32_t* r) { Fp x, y, z; memcpy(x.v, a, 52); memcpy(y.v, b, 52); fe_sub_cneg<FpTag, 4>(z, x, y, neg != 0); memcpy(r, z.v, 52); }
+void fc_fp_sub_reduce3_rawsum(const uint32_t* a, const uint32_t* b1, const uint32_t* b2, uint32_t* r) {
+    uint32_t tab[9 * FP_N]; fe_fill_multiples<FpTag>(tab);
+    Fp x, y1, y2, u, z; memcpy(x.v, a, 52); memcpy(y1.v, b1, 52); memcpy(y2.v, b2, 52);
+    fe_add_raw(u, y1, y2); fe_sub_reduce<FpTag, 3>(z, x, u, tab); memcpy(r, z.v, 52); }
+void fc_fp_sub_reduce2(const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    uint32_t tab[9 * FP_N]; fe_fill_multiples<FpTag>(tab);
+    Fp x, y, z; memcpy(x.v, a, 52); memcpy(y.v, b, 52); fe_sub_reduce<FpTag, 2>(z, x, y, tab); memcpy(r, z.v, 52); }
+// one batch of affine additions exactly as the fused backward loop does them; negs[i] != 0 adds -pts[i]
+int fc_g1_affine_batch_add_fused(const uint8_t* accs, const uint8_t* pts, const uint8_t* negs, int n, uint8_t* out) {
+    G1Affine A[64], B[64]; Fp pre[64];
+    uint32_t tab[9 * FP_N]; fe_fill_multiples<FpTag>(tab);
+    if (n > 64) return -1;
+    for (int i = 0; i < n; i++) if (g1_decompress(A[i], accs + 48 * i) || g1_decompress(B[i], pts + 48 * i)) return -1;
+    Fp P; fe_const<FpTag, FP_ONE>(P);
+    for (int k = 0; k < n; k++) { Fp d; fe_sub<FpTag, 2>(d, B[k].x, A[k].x); if (fe_is_zero_mod(d)) return -2; pre[k] = P; fe_mul(P, P, d); }
+    Fp I; fe_inv_safegcd(I, P);
+    for (int k = n - 1; k >= 0; k--) {
+        Fp inv, d, lam, t, u;
+        fe_mul(inv, I, pre[k]);
+        fe_sub<FpTag, 2>(d, B[k].x, A[k].x); fe_mul(I, I, d);
+        fe_add_raw(u, A[k].x, B[k].x);
+        fe_sub_cneg<FpTag, 4>(t, B[k].y, A[k].y, negs[k] != 0);
+        fe_mul(lam, t, inv);
+        fe_sqr(t, lam);
+        fe_sub_reduce<FpTag, 3>(t, t, u, tab);
+        fe_sub<FpTag, 2>(u, A[k].x, t); fe_mul(u, lam, u);
+        fe_sub_reduce<FpTag, 2>(u, u, A[k].y, tab);
+        A[k].x = t; A[k].y = u;
+        g1_compress_affine(out + 48 * k, A[k]);
+    }
+    return 0; }
 void fc_fp_reduce_loose(const uint32_t* a, uint32_t* r) { Fp x; memcpy(x.v, a, 52); fe_reduce_loose<FpTag>(x); memcpy(r, x.v, 52); }
 // k*P by double-and-add through madd/dbl (exercises long chains with loose bounds)
 int fc_g1_mul_u64(const uint8_t* a, uint64_t k, uint8_t* out) {

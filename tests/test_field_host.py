@@ -13,12 +13,20 @@ P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB1
 R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 
 
+def build(form=None):
+    """The headers as the library compiles them (form None), or with one of field30.cuh's other
+    Montgomery-product formulations (-DRK_MUL_FORM=n)."""
+    so = SO if form is None else SO.replace(".so", "_form%d.so" % form)
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so]
+                          + ([] if form is None else ["-DRK_MUL_FORM=%d" % form])
+                          + [os.path.join(HERE, "native", "fieldcheck.cpp")])
+    return ctypes.CDLL(so)
+
+
 @pytest.fixture(scope="module")
 def L():
-    os.makedirs(os.path.dirname(SO), exist_ok=True)
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO,
-                           os.path.join(HERE, "native", "fieldcheck.cpp")])
-    return ctypes.CDLL(SO)
+    return build()
 
 
 def limbs(v, n):
@@ -29,8 +37,12 @@ def val(a, bits=30):
     return sum(int(x) << (bits * i) for i, x in enumerate(a))
 
 
+@pytest.mark.parametrize("form", [None, 0, 1, 2])
 @pytest.mark.parametrize("name,mod,n", [("fp", P, 13), ("fr", R, 9)])
-def test_montgomery_mul_sqr(L, name, mod, n):
+def test_montgomery_mul_sqr(form, name, mod, n):
+    """Every formulation of the Montgomery product (field30.cuh RK_MUL_FORM), worst-case column
+    sums first: a wrapped 64-bit column shows up as a wrong product."""
+    L = build(form)
     rnd = random.Random(n)
     MR = 1 << (30 * n)
     mul, sqr = getattr(L, "fc_%s_mul" % name), getattr(L, "fc_%s_sqr" % name)
@@ -156,6 +168,32 @@ def test_reduce_loose(L):
             assert r < P * 1.0001
 
 
+def test_fused_limb_passes(L):
+    """field30.cuh's fused passes (k_msm_affine with RK_AFF_FUSE): conditional negation folded into a
+    subtraction, and subtraction + loose reduction in one pass with a raw (unnormalised) subtrahend."""
+    rnd = random.Random(78)
+    edge = [0, 1, P - 1, P, P + 1, 2 * P - 1, 2 * P, (1 << 360) - 1, 1 << 360]
+    for t in range(6000):
+        a = edge[t % len(edge)] if t < 90 else rnd.randrange(2 * P)         # +-a - b + 4p needs a + b <= 4p
+        b = edge[(t // len(edge)) % len(edge)] if t < 90 else rnd.randrange(2 * P)
+        for neg in (0, 1):
+            out = (ctypes.c_uint32 * 13)()
+            L.fc_fp_sub_cneg4(limbs(a, 13), limbs(b, 13), neg, out)
+            assert val(out) == (-a if neg else a) - b + 4 * P and all(v < (1 << 30) for v in out)
+        # x3-shaped: a - (b1 + b2) + 3p, b1 + b2 <= 3p, the sum NOT normalised
+        a = edge[t % len(edge)] if t < 90 else rnd.randrange(int(1.2 * P))
+        b1, b2 = (edge[(t // 9) % 9] % (P + 2), edge[(t // 3) % 9] % (P + 2)) if t < 90 else (rnd.randrange(int(1.5 * P)), rnd.randrange(int(1.5 * P)))
+        out = (ctypes.c_uint32 * 13)()
+        L.fc_fp_sub_reduce3_rawsum(limbs(a, 13), limbs(b1, 13), limbs(b2, 13), out)
+        r = val(out)
+        assert (r - (a - b1 - b2)) % P == 0 and 0 <= r < max(P + (12 << 360), a + 1) and all(v < (1 << 30) for v in out), (a, b1, b2, r)
+        # y3-shaped: a - b + 2p, b <= 2p
+        b = edge[(t // 9) % 9] if t < 90 else rnd.randrange(2 * P)
+        L.fc_fp_sub_reduce2(limbs(a, 13), limbs(b, 13), out)
+        r = val(out)
+        assert (r - (a - b)) % P == 0 and 0 <= r < max(P + (12 << 360), a + 1) and all(v < (1 << 30) for v in out), (a, b, r)
+
+
 def test_affine_batch_addition_pieces(L, pyoracle):
     """The two halves of k_msm_affine's arithmetic on the host: one batch of affine additions
     under a shared safegcd inversion (forward prefix products, backward peel), and the slow path
@@ -170,6 +208,12 @@ def test_affine_batch_addition_pieces(L, pyoracle):
     assert rc == 0
     for i in range(n):
         assert out.raw[48 * i:48 * i + 48] == o.g1_compress(o.g1_add(accs[i], pts[i])), i
+    # the fused backward loop (RK_AFF_FUSE), with signs: acc[i] +- pts[i]
+    negs = bytes(rnd.randrange(2) for _ in range(n))
+    rc = L.fc_g1_affine_batch_add_fused(b"".join(map(o.g1_compress, accs)), b"".join(map(o.g1_compress, pts)), negs, n, out)
+    assert rc == 0
+    for i in range(n):
+        assert out.raw[48 * i:48 * i + 48] == o.g1_compress(o.g1_add(accs[i], o.g1_neg(pts[i]) if negs[i] else pts[i])), i
     # equal x is refused by the batch and done by the slow path
     assert L.fc_g1_affine_batch_add(o.g1_compress(accs[0]), o.g1_compress(accs[0]), 1, out) == -2
     assert L.fc_g1_affine_batch_add(o.g1_compress(accs[0]), o.g1_compress(o.g1_neg(accs[0])), 1, out) == -2
