@@ -239,7 +239,10 @@ def msm_roofline(stats, msm_kernel_ms, peak, inputs, world_value_per_gpu):
 
     frac        executed multiply instructions (IMAD.WIDE / IMAD, thread level, from the committed
                 ncu opcode histogram) per second / measured peak.  This is a pipe-utilisation number.
-    slot_frac   the same with IMAD.WIDE Rd,Ra,Rb,Rc64 counted twice (it issues at half rate on B200).
+    slot_frac   the same with every IMAD.WIDE that has a 64-bit register addend counted twice: both the
+                Ra,Rb,Rc64 form (product rows) and the Ra,imm,Rc64 form (reduction rows) issue at half rate
+                on B200 (29 / 31 per clock per SM, profiles/r02/wide_operands3_ubench.txt).  This is the
+                occupancy of the multiply pipe the instruction mix implies; it should agree with pipe_busy.
     model_frac  SURVEY.md 8(d) work model (540.7 M IMAD per MSM) per second / peak: a SPEED-UP over the
                 model algorithm, not a utilisation -- the kernel executes far fewer multiplies.
     pipe_busy   sm__pipe_fmaheavy_cycles_active of the same ncu capture."""

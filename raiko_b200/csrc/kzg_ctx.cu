@@ -336,7 +336,12 @@ rk_status alloc_slots(DeviceCtx* d) {
     // measured 13 % slower), and the per-chunk fixed costs (hash latency, finalize, launch gaps)
     // amortise over more blobs.
     // 2 slots x (blobs + quotients: 128 KiB each, inversion scratch: 144 KiB) per blob = 3.8 GB.
-    d->chunk = 4 * d->sm_count * d->warps_per_sm;
+    d->chunk = std::max(4 * d->sm_count * d->warps_per_sm, 2 * d->sm_count * d->aff_warps);
+    if (const char* e = getenv("RAIKO_KZG_L2_FETCH")) {
+        // experiment knob: L2 fetch granularity for DRAM misses (32 / 64 / 128 B); table entries are random
+        // 96-byte gathers, so a coarser granule than a sector over-fetches
+        CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
+    }
     if (const char* e = getenv("RAIKO_KZG_CHUNK")) {
         int v = atoi(e);
         if (v >= 1 && v <= 16384) d->chunk = v;

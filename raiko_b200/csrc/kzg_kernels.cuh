@@ -181,6 +181,14 @@ __device__ __forceinline__ void msm_body(const MsmParams& prm) {
 }
 #endif  // RK_TU_MSM (xyzz body)
 
+// 1: the additions of a SHA-256 round as IMADs on the multiply pipe in the rounds-only warps (sha256.cuh).
+// Measured on B200 (profiles/r02/): no gain -- a lone warp issues an instruction every ~2 cycles whatever
+// the pipe mix (2.26 ms per 128 KiB chain either way) -- and beside the MSM (6-blob requests) it competes
+// for the pipe the MSM saturates: 3.43 ms against 3.28 ms.  Kept off.
+#ifndef RK_SHA_FMA_ADDS
+#define RK_SHA_FMA_ADDS 0
+#endif
+
 // ---------------------------------------------------------------------------
 // k_msm_affine: the same MSM with batched AFFINE additions.
 //
@@ -237,7 +245,7 @@ constexpr int MSM_AFF_MAX_K = 64;
 // subtraction, subtraction + loose reduction in one pass against a shared-memory table of multiples
 // of p); 0: one pass per operation, as in round 1.
 #ifndef RK_AFF_FUSE
-#define RK_AFF_FUSE 0
+#define RK_AFF_FUSE 1
 #endif
 constexpr int MSM_AFF_THREADS = RK_AFF_THREADS;
 
@@ -746,7 +754,7 @@ __global__ void __launch_bounds__(64) k_sha_blob_duo(const uint8_t* blobs, int n
                 blk[15] = (uint32_t)BLOB_BYTES * 8u;
             }
             uint32_t w[64];
-            sha256_schedule(w, blk);
+            sha256_schedule_k(w, blk);
 #pragma unroll
             for (int i = 0; i < 64; i++) wbuf[b & 1][i][lane] = w[i];
         }
@@ -754,7 +762,7 @@ __global__ void __launch_bounds__(64) k_sha_blob_duo(const uint8_t* blobs, int n
             uint32_t w[64];
 #pragma unroll
             for (int i = 0; i < 64; i++) w[i] = wbuf[(b - 1) & 1][i][lane];
-            sha256_rounds(st, w);
+            sha256_rounds<RK_SHA_FMA_ADDS != 0>(st, w, (uint32_t)(nblobs > 0));
         }
         __syncthreads();
     }
@@ -1453,7 +1461,7 @@ __global__ void __launch_bounds__(64) k_batch_challenge(const uint8_t* c, const 
                 if (pad_word >= 0 && pad_word < 16) blk[pad_word] = 0x80000000u;
                 if (b == nblk - 1) { const unsigned long long bits = (unsigned long long)bytes * 8ull; blk[14] = (uint32_t)(bits >> 32); blk[15] = (uint32_t)bits; }
                 uint32_t w[64];
-                sha256_schedule(w, blk);
+                sha256_schedule_k(w, blk);
 #pragma unroll
                 for (int i = 0; i < 64; i++) wbuf[g & 1][lane][i] = w[i];
             }
@@ -1461,7 +1469,7 @@ __global__ void __launch_bounds__(64) k_batch_challenge(const uint8_t* c, const 
         if (warp == 0 && lane == 0 && g > 0) {        // consumer: the 32 blocks of group g - 1, in order
             const long long b0 = 32 * (g - 1);
             const int cnt = (int)(nblk - b0 < 32 ? nblk - b0 : 32);
-            for (int j = 0; j < cnt; j++) sha256_rounds(st, wbuf[(g - 1) & 1][j]);
+            for (int j = 0; j < cnt; j++) sha256_rounds<RK_SHA_FMA_ADDS != 0>(st, wbuf[(g - 1) & 1][j], (uint32_t)(n > 0));
         }
         __syncthreads();
     }

@@ -37,23 +37,50 @@ RK_HD void sha256_init(Sha256State& s) {
     s.h[4] = 0x510e527fu; s.h[5] = 0x9b05688cu; s.h[6] = 0x1f83d9abu; s.h[7] = 0x5be0cd19u;
 }
 
-// One round, written so that the dependent chain through e (and a) is three instructions
-// deep -- rotate, 3-input xor, 3-input add -- instead of the six of the textbook statement:
-// h and d are values of e and a from three rounds earlier, so h + K + W and d + h + K + W are
-// formed off the critical path and the new e and a each take ONE 3-input add after Sigma / Ch.
-// A single SHA-256 chain is pure latency (the blob hash is the critical path of a 6-blob request):
-// used by the rounds-only half of the two-warp hash, 6-blob commit+prove 3.49 -> 3.25 ms.
+// a + b on the multiply pipe (IMAD.IADD) instead of the ALU pipe.  One warp alone on a scheduler --
+// the rounds half of the two-warp hash -- is bound by the ALU pipe's issue rate (a warp instruction
+// every two cycles), not by its dependent chain: of the ~14 ALU instructions of a round only the six
+// rotates and four three-input logic ops have to be there, so the additions go to the other pipe.
+// `one` must be the value 1 in a register whose content neither the compiler nor the assembler can
+// know (the kernels pass `nblobs > 0`): with a literal 1 ptxas folds pairs of these back into
+// three-input IADD3s on the ALU pipe.
+RK_HD uint32_t sha_add_fma(uint32_t a, uint32_t b, uint32_t one) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+#else
+    return a * one + b;
+#endif
+}
+
+// One round, written so that the dependent chain through e (and a) is short -- rotate, 3-input xor,
+// two additions -- instead of the six steps of the textbook statement: h and d are values of e and a
+// from three rounds earlier, so h + K + W and d + h + K + W are formed off the critical path.
+// A single SHA-256 chain is pure latency (the blob hash is the critical path of a 6-blob request).
+// FMA_ADDS: additions as IMAD.IADD (see sha_add_fma); used by the rounds-only half of the two-warp hash.
+template <bool FMA_ADDS = false>
 RK_HD void sha256_round(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t& e, uint32_t& f, uint32_t& g,
-                        uint32_t& h, uint32_t kw) {
-    const uint32_t hkw = h + kw;
-    const uint32_t dhkw = d + hkw;
+                        uint32_t& h, uint32_t kw, uint32_t one = 1u) {
     const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
     const uint32_t ch = g ^ (e & (f ^ g));
     const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
     const uint32_t mj = (a & b) | (c & (a | b));
-    const uint32_t e_new = dhkw + S1 + ch;
-    const uint32_t t1 = hkw + S1 + ch;
-    const uint32_t a_new = t1 + S0 + mj;
+    uint32_t e_new, a_new;
+    if (FMA_ADDS) {
+        const uint32_t hkw = sha_add_fma(h, kw, one);
+        const uint32_t dhkw = sha_add_fma(d, hkw, one);
+        const uint32_t sc = sha_add_fma(S1, ch, one);
+        const uint32_t sm = sha_add_fma(S0, mj, one);
+        e_new = sha_add_fma(dhkw, sc, one);
+        a_new = sha_add_fma(sha_add_fma(hkw, sc, one), sm, one);
+    } else {
+        const uint32_t hkw = h + kw;
+        const uint32_t dhkw = d + hkw;
+        e_new = dhkw + S1 + ch;
+        const uint32_t t1 = hkw + S1 + ch;
+        a_new = t1 + S0 + mj;
+    }
     h = g; g = f; f = e; e = e_new; d = c; c = b; b = a; a = a_new;
 }
 
@@ -96,11 +123,19 @@ RK_HD void sha256_schedule(uint32_t* wout /* [64] */, const uint32_t (&blk)[16])
         wout[i] = w[i & 15];
     }
 }
-RK_HD void sha256_rounds(Sha256State& s, const uint32_t* w /* [64], expanded */) {
+// the same with the round constants added: kw[i] = K[i] + w[i], what sha256_rounds consumes
+RK_HD void sha256_schedule_k(uint32_t* kwout /* [64] */, const uint32_t (&blk)[16]) {
+    sha256_schedule(kwout, blk);
+#pragma unroll
+    for (int i = 0; i < 64; i++) kwout[i] += SHA256_K::at(i);
+}
+// kw[i] = K[i] + w[i] (the schedule half adds the round constants)
+template <bool FMA_ADDS = false>
+RK_HD void sha256_rounds(Sha256State& s, const uint32_t* kw /* [64], expanded, round constants added */, uint32_t one = 1u) {
     uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
-        sha256_round(a, b, c, d, e, f, g, h, SHA256_K::at(i) + w[i]);
+        sha256_round<FMA_ADDS>(a, b, c, d, e, f, g, h, kw[i], one);
     }
     s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }

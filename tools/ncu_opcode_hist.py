@@ -7,14 +7,17 @@ roofline is quoted against is a measured number and not a constant typed into be
 
 Classes (B200, measured rates in profiles/r01/*_r01.txt):
   imad_wide_rr64   IMAD.WIDE[.U32] Rd, Ra, Rb, Rc     two register multiplicands + 64-bit register addend: HALF rate (29/clk/SM)
-  imad_wide_rz     IMAD.WIDE[.U32] Rd, Ra, Rb, RZ     no addend: full rate
-  imad_wide_imm    IMAD.WIDE[.U32] Rd, Ra, imm|c[], Rc constant multiplicand: full rate
+  imad_wide_rz     IMAD.WIDE[.U32] Rd, Ra, Rb|imm, RZ no addend: full rate
+  imad_wide_imm    IMAD.WIDE[.U32] Rd, Ra, imm|c[], Rc constant multiplicand + 64-bit register addend: HALF rate too
+                   (31/clk/SM, profiles/r02/wide_operands3_ubench.txt; round 1 took it for full rate from a
+                   microbenchmark whose repeated immediate products the compiler had merged)
   imad32           IMAD / IMAD.X / IMAD.SHL / IMAD.IADD / IMAD.HI ... 32-bit forms (IMAD.MOV counted as mov)
   lop_shf          LOP3 / SHF (share the multiply pipe's issue port: 58/clk/SM)
   iadd             IADD3 / IADD3.X / IADD
   ldst_global, ldst_shared, ldst_local, barrier, control, other
-`mul_pipe_slots` = 2 * imad_wide_rr64 + imad_wide_rz + imad_wide_imm + imad32 (issue slots on the
-integer-multiply pipe), counted per warp instruction.
+`mul_pipe_slots` = 2 * (imad_wide_rr64 + imad_wide_imm) + imad_wide_rz + imad32 (issue slots on the
+integer-multiply pipe: an IMAD.WIDE with a 64-bit register addend occupies it twice as long), counted per
+warp instruction.
 """
 import argparse
 import collections
@@ -37,10 +40,10 @@ def classify(sass: str) -> str:
             ops = [o.strip() for o in s[len(op):].split(",")]
             b = ops[2] if len(ops) > 2 else ""          # Rd, Ra, Rb, Rc
             c = ops[3] if len(ops) > 3 else ""
+            if c.startswith("RZ"):
+                return "imad_wide_rz"                    # no addend (any multiplicand): full rate
             if not b.lstrip("-~|").startswith("R") or b.startswith("RZ"):
                 return "imad_wide_imm"                   # immediate, constant bank or uniform multiplicand
-            if c.startswith("RZ"):
-                return "imad_wide_rz"
             return "imad_wide_rr64"
         return "imad32"
     if base in ("LOP3", "SHF", "LOP", "SHL", "SHR", "PRMT", "BMSK", "SGXT", "LEA"):
@@ -93,7 +96,7 @@ def histogram(report: str, launch: int = 0) -> dict:
         thread_total += int(r[i_thr] or 0)
         hist[classify(r[i_src])] += n
         ops[PRED.sub("", r[i_src].strip()).split()[0]] += n
-    slots = 2 * hist["imad_wide_rr64"] + hist["imad_wide_rz"] + hist["imad_wide_imm"] + hist["imad32"]
+    slots = 2 * (hist["imad_wide_rr64"] + hist["imad_wide_imm"]) + hist["imad_wide_rz"] + hist["imad32"]
     mul_inst = hist["imad_wide_rr64"] + hist["imad_wide_rz"] + hist["imad_wide_imm"] + hist["imad32"]
     return {
         "kernel": blk["name"], "report": report,
