@@ -1493,8 +1493,11 @@ __global__ void __launch_bounds__(64) k_batch_challenge(const uint8_t* c, const 
 __global__ void __launch_bounds__(64) k_verify_terms(const Fr* r_mont, const uint8_t* z, const uint8_t* y, const G1Affine* cs,
                                                       const int* c_inf, const G1Affine* ps, const int* p_inf, int n, G1Xyzz* out_a,
                                                       G1Xyzz* out_e, int* err) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = gid >> 2, j = gid & 3;
+    // grid = (ceil(n / 64), 4): blockIdx.y = j selects the term, so every warp walks ONE kind of scalar
+    // multiplication (with j in the lane index the three branches below ran one after the other in
+    // every warp: 16.3 ms per 4096 blobs against 16.3 / 3 and less with the windowed ladder).
+    //   j = 0: r^i proof_i    1: (r^i z_i) proof_i    2: r^i C_i    3: -(r^i y_i) G
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= n) return;
     Fr base = *r_mont, ri, kc;
     fe_const<FrTag, FR_ONE>(ri);
@@ -1512,16 +1515,15 @@ __global__ void __launch_bounds__(64) k_verify_terms(const Fr* r_mont, const uin
     fe_from_mont(kc, ri);
     uint32_t k[8];
     fe_pack<FrTag>(k, kc);
+    G1Affine base_pt;
+    bool inf;
+    if (j <= 1) { base_pt = ps[i]; inf = p_inf[i] != 0; }
+    else if (j == 2) { base_pt = cs[i]; inf = c_inf[i] != 0; }
+    else { fe_const<FpTag, FP_GEN_X>(base_pt.x); fe_const<FpTag, FP_GEN_Y>(base_pt.y); inf = false; }
     G1Xyzz t;
     g1_set_inf(t);
-    if (j <= 1) { if (!p_inf[i]) g1_scalar_mul(t, ps[i], k); }
-    else if (j == 2) { if (!c_inf[i]) g1_scalar_mul(t, cs[i], k); }
-    else {
-        G1Affine g;
-        fe_const<FpTag, FP_GEN_X>(g.x); fe_const<FpTag, FP_GEN_Y>(g.y);
-        g1_scalar_mul(t, g, k);
-        if (!g1_is_inf(t)) fe_neg<FpTag, 6>(t.y, t.y);
-    }
+    if (!inf) g1_scalar_mul_w4(t, base_pt, k);
+    if (j == 3 && !g1_is_inf(t)) fe_neg<FpTag, 6>(t.y, t.y);
     if (j == 0) out_a[i] = t; else out_e[3 * (size_t)i + (j - 1)] = t;
 }
 

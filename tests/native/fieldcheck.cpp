@@ -211,6 +211,12 @@ static int load_xy(G1Affine& a, const uint8_t* xy) {
     fe_sub<FpTag, 4>(t, l, r3);
     return fe_is_zero_mod(t) ? 0 : -1;
 }
+// k * P for a 256-bit k (8 little-endian words): the bitwise ladder and the 4-bit-window one of k_verify_terms
+int fc_g1_scalar_mul(const uint8_t* a, const uint32_t* k, int windowed, uint8_t* out) {
+    G1Affine q; if (g1_decompress(q, a)) return -1;
+    G1Xyzz t;
+    if (windowed) g1_scalar_mul_w4(t, q, k); else g1_scalar_mul(t, q, k);
+    g1_compress(out, t); return 0; }
 int fc_g1_in_subgroup_fast(const uint8_t* xy) { G1Affine a; if (load_xy(a, xy)) return -1; return g1_in_subgroup(a) ? 1 : 0; }
 int fc_g1_in_subgroup_slow(const uint8_t* xy) {
     G1Affine a; if (load_xy(a, xy)) return -1;

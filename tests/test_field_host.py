@@ -168,6 +168,23 @@ def test_reduce_loose(L):
             assert r < P * 1.0001
 
 
+def test_scalar_multiplication_ladders(L, pyoracle):
+    """g1.cuh's two variable-base scalar multiplications (bitwise double-and-add, and the 4-bit fixed
+    window the verification kernel uses) against the big-integer oracle, edge scalars included."""
+    o, _ = pyoracle
+    rnd = random.Random(13)
+    pts = [o.g1_mul(o.G1_GEN, rnd.randrange(1, R)) for _ in range(3)]
+    ks = [0, 1, 2, 15, 16, 17, R - 1, R, R + 1, (1 << 256) - 1, 0xF0F0 << 240, 1 << 255] + [rnd.randrange(1 << 256) for _ in range(6)]
+    for pt in pts:
+        for k in ks:
+            words = (ctypes.c_uint32 * 8)(*[(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+            want = o.g1_compress(o.g1_mul(pt, k % R) if k % R else None)
+            for windowed in (0, 1):
+                out = ctypes.create_string_buffer(48)
+                assert L.fc_g1_scalar_mul(o.g1_compress(pt), words, windowed, out) == 0
+                assert out.raw == want, (hex(k), windowed)
+
+
 def test_fused_limb_passes(L):
     """field30.cuh's fused passes (k_msm_affine with RK_AFF_FUSE): conditional negation folded into a
     subtraction, and subtraction + loose reduction in one pass with a raw (unnormalised) subtrahend."""

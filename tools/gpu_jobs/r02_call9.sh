@@ -1,0 +1,7 @@
+#!/bin/bash
+# Round 2, GPU call 9 (1 x B200): verification after the uniform-warp / 4-bit-window r-power terms.
+set -u
+mkdir -p gpurun_out
+( time python -m pytest tests/test_gpu_verify.py tests/test_gpu_callers.py tests/test_gpu_cpp_host.py -m gpu -x -q ) > gpurun_out/r02_c9_pytest_verify.txt 2>&1
+echo "pytest rc=$?" >> gpurun_out/r02_c9_pytest_verify.txt; tail -4 gpurun_out/r02_c9_pytest_verify.txt
+RAIKO_KZG_VERIFY_TRACE=1 python tests/tools/verify_trace.py 4096 > gpurun_out/r02_c9_verify_lanes.txt 2>&1; tail -8 gpurun_out/r02_c9_verify_lanes.txt
