@@ -153,7 +153,7 @@ struct DeviceCtx {
     Fr* roots = nullptr;
     G1Affine* g1_aff = nullptr;            // 4096 setup points, affine Montgomery
     LineStep* g2_lines = nullptr;          // device 0 only: Miller-loop lines of [s]G2 and the G2 generator
-    bool pairing_lanes = true;             // RAIKO_KZG_PAIRING_LANES=0: single-thread pairing check
+    int pairing_lanes = 2;                 // RAIKO_KZG_PAIRING_LANES: 2 = CTA-wide (144 threads), 1 = one warp (12 lanes), 0 = single thread
     cudaStream_t s_main = nullptr, s_sha = nullptr, s_in = nullptr, s_out = nullptr;
     int chunk = 0;
     int max_partials = 0;
@@ -931,7 +931,8 @@ rk_status verify_finish(rk_kzg_ctx* ctx, DeviceCtx* d, VerifyState& v, const uin
     launch_k_verify_reduce_partial(VR_PARTS, VR_THREADS, 0, st, v.d_a, n, v.d_e, 3 * n, v.d_part, v.d_part + VR_PARTS);
     launch_k_verify_reduce(1, VR_THREADS, 0, st, v.d_part, v.d_part + VR_PARTS, VR_PARTS, v.d_pair, v.d_pinf);
     mark(4);
-    if (d->pairing_lanes && d->g2_lines) launch_k_pairing_check_lanes(1, 32, 0, st, v.d_pair, v.d_pinf, d->g2_lines, v.d_flags + 3);
+    if (d->pairing_lanes >= 2 && d->g2_lines) launch_k_pairing_check_cta(1, PAIRING_CTA_THREADS, 0, st, v.d_pair, v.d_pinf, d->g2_lines, v.d_flags + 3);
+    else if (d->pairing_lanes && d->g2_lines) launch_k_pairing_check_lanes(1, 32, 0, st, v.d_pair, v.d_pinf, d->g2_lines, v.d_flags + 3);
     else launch_k_pairing_check(1, 1, 0, st, v.d_pair, v.d_pinf, v.d_g2, v.d_g2 + 192, v.d_flags + 3);
     mark(5);
     d->stats.total_launches += 5;
@@ -1088,7 +1089,7 @@ rk_status rk_kzg_ctx_create_ex(const uint8_t* settings, size_t len, const int* d
     {
         // fixed-argument pairing precomputation on the verification device (ctx device 0)
         DeviceCtx* d = ctx->devs[0];
-        if (const char* e = getenv("RAIKO_KZG_PAIRING_LANES")) d->pairing_lanes = atoi(e) != 0;
+        if (const char* e = getenv("RAIKO_KZG_PAIRING_LANES")) d->pairing_lanes = atoi(e);
         rk_status st = RK_OK;
         cudaError_t ce = cudaSetDevice(d->dev);
         uint8_t* d_g2 = nullptr;

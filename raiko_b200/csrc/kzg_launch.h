@@ -52,7 +52,8 @@ constexpr size_t PAIRING_LINES_BYTES = 2 * 68 * 4 * sizeof(Fp);   // 2 fixed G2 
 #define RK_KERNELS_PAIRING(X)                                                                  \
     X(k_pairing_check, (const G1Affine* pts, const int* inf, const uint8_t* g2_s_be, const uint8_t* g2_gen_be, int* out_ok), (pts, inf, g2_s_be, g2_gen_be, out_ok)) \
     X(k_pairing_precompute, (const uint8_t* g2_s_be, const uint8_t* g2_gen_be, LineStep* out), (g2_s_be, g2_gen_be, out)) \
-    X(k_pairing_check_lanes, (const G1Affine* pts, const int* inf, const LineStep* lines, int* out_ok), (pts, inf, lines, out_ok))
+    X(k_pairing_check_lanes, (const G1Affine* pts, const int* inf, const LineStep* lines, int* out_ok), (pts, inf, lines, out_ok)) \
+    X(k_pairing_check_cta, (const G1Affine* pts, const int* inf, const LineStep* lines, int* out_ok), (pts, inf, lines, out_ok))
 
 #define RK_DECLARE_LAUNCH(name, params, args) \
     void launch_##name(dim3 grid, dim3 block, size_t smem, cudaStream_t st, RK_UNPAREN params);

@@ -404,25 +404,32 @@ constexpr int PAIRING_STEPS = 68;                  // 63 doublings + 5 additions
 
 struct LineStep { Fp l0, l6, a, b; };              // line = l0 + l6 w^6 + (a xP) w^2 + (b xP) w^8 + yP w^3
 
+// Sub-lanes.  The products of one lane are independent, so a lane may be played by S threads
+// ("sub-lanes"): sub-lane s takes the products whose running number is congruent to s modulo S and
+// the partial sums are added up afterwards (lp_collect).  S = 1: the whole lane, as before.
+// S = 12 turns an Fp12 product into ONE Fp product per thread on 144 threads.
+
 // lane k: raw coefficients t[k] (lo) and t[k + 12] (hi) of a * b
-RK_HD_NOINLINE void fp12_mul_lane(int k, const Fp* a, const Fp* b, Fp& lo, Fp& hi) {
+RK_HD_NOINLINE void fp12_mul_lane(int k, const Fp* a, const Fp* b, Fp& lo, Fp& hi, int s = 0, int S = 1) {
     fe_zero(lo); fe_zero(hi);
 #pragma unroll 1
-    for (int i = 0; i < 12; i++) {
+    for (int i = s; i < 12; i += S) {
         Fp m;
         if (i <= k) { fp_mul_sel<true>(m, a[i], b[k - i]); fq_add(lo, lo, m); }
         else { fp_mul_sel<true>(m, a[i], b[k + 12 - i]); fq_add(hi, hi, m); }
     }
 }
 // lane k: the same for a * a, cross terms once and doubled (7 products)
-RK_HD_NOINLINE void fp12_sqr_lane(int k, const Fp* a, Fp& lo, Fp& hi) {
+RK_HD_NOINLINE void fp12_sqr_lane(int k, const Fp* a, Fp& lo, Fp& hi, int s = 0, int S = 1) {
     fe_zero(lo); fe_zero(hi);
+    int q = 0;
     for (int pass = 0; pass < 2; pass++) {
         const int n = pass == 0 ? k : k + 12;
         Fp& t = pass == 0 ? lo : hi;
         const int i0 = n > 11 ? n - 11 : 0;
 #pragma unroll 1
-        for (int i = i0; 2 * i <= n; i++) {
+        for (int i = i0; 2 * i <= n; i++, q++) {
+            if (q % S != s) continue;
             const int j = n - i;
             Fp m;
             if (i == j) fp_sqr_sel<true>(m, a[i]);
@@ -432,11 +439,11 @@ RK_HD_NOINLINE void fp12_sqr_lane(int k, const Fp* a, Fp& lo, Fp& hi) {
     }
 }
 // lane k: the same for a * (l0 + l2 w^2 + l3 w^3 + l6 w^6 + l8 w^8) (5 products)
-RK_HD_NOINLINE void fp12_line_lane(int k, const Fp* a, const LineCoeffs& l, Fp& lo, Fp& hi) {
+RK_HD_NOINLINE void fp12_line_lane(int k, const Fp* a, const LineCoeffs& l, Fp& lo, Fp& hi, int s = 0, int S = 1) {
     fe_zero(lo); fe_zero(hi);
     const int es[5] = {0, 2, 3, 6, 8};
 #pragma unroll 1
-    for (int q = 0; q < 5; q++) {
+    for (int q = s; q < 5; q += S) {
         const int e = es[q];
         const Fp& c = e == 0 ? l.l0 : e == 2 ? l.l2 : e == 3 ? l.l3 : e == 6 ? l.l6 : l.l8;
         Fp m;
@@ -460,12 +467,12 @@ RK_HD_NOINLINE void fp12_fold_lane(int k, const Fp* t, Fp& out) {
 }
 // lane k: coefficient k of a^(p^e) (TAB = FP12_FROB1 / FP12_FROB2): two products
 template <class TAB>
-RK_HD_NOINLINE void fp12_frob_lane(int k, const Fp* a, Fp& out) {
+RK_HD_NOINLINE void fp12_frob_lane(int k, const Fp* a, Fp& out, int s = 0, int S = 1) {
     const int half = k >= 6 ? 13 : 0;
     Fp acc;
     fe_zero(acc);
 #pragma unroll 1
-    for (int q = 0; q < 2; q++) {
+    for (int q = s; q < 2; q += S) {
         const int j = (k % 6) + 6 * q;
         Fp c, m;
         for (int l = 0; l < FP_N; l++) c.v[l] = frob_word<TAB>(j * 26 + half + l);
@@ -515,43 +522,80 @@ RK_HD_NOINLINE void pairing_precompute_lines(LineStep* out /* [PAIRING_STEPS] */
 }
 
 // ---- the check itself, written once against an "exchange" policy X: -------------------------
-//   X::lanes()            how many lanes this invocation runs (device: 1 = this thread; host: 12)
-//   X::lane(i)            lane index of the i-th of them
+//   X::LANES              how many (lane, sub-lane) threads this invocation plays (device: 1 = this thread)
+//   X::SUB                sub-lanes per lane (threads sharing the products of one coefficient)
+//   X::lane(i), X::sub(i) lane and sub-lane index of the i-th of them
 //   X::publish(slot, k, v) / X::sync() / X::read(slot) -> const Fp*   the 12-coefficient exchange
-// Device: lanes are threads, slots live in shared memory, sync = __syncwarp.  Host: one thread
-// plays all 12 lanes phase by phase.  A distributed Fp12 value is `Fp v[X::lanes()]`.
+//   X::publish_part(s, n, v) / X::read_part(s) -> const Fp* [24]      partial raw coefficients of sub-lane s
+// Device: lanes are threads, slots live in shared memory, sync = a warp or CTA barrier.  Host: one
+// thread plays all of them phase by phase.  A distributed Fp12 value is `Fp v[X::LANES]`; the sub-lanes
+// of a lane all hold the lane's coefficient.
 template <class X>
 struct LaneFp12 {
     Fp c[X::LANES];
 };
+// raw coefficients (lo, hi) of every played thread -> t[0..23] in slots 2 | 3
+template <class X> RK_HD void lp_collect(X& x, const Fp* lo, const Fp* hi) {
+    if (X::SUB == 1) {
+        for (int i = 0; i < X::LANES; i++) { x.publish(2, x.lane(i), lo[i]); x.publish(3, x.lane(i), hi[i]); }
+        x.sync();
+        return;
+    }
+    for (int i = 0; i < X::LANES; i++) { x.publish_part(x.sub(i), x.lane(i), lo[i]); x.publish_part(x.sub(i), 12 + x.lane(i), hi[i]); }
+    x.sync();
+    for (int i = 0; i < X::LANES; i++) {
+        const int j = x.sub(i);                         // sub-lane 0 adds up t[k], sub-lane 1 t[12 + k]
+        if (j > 1) continue;
+        const int n = 12 * j + x.lane(i);
+        Fp acc = x.read_part(0)[n];
+        for (int s = 1; s < X::SUB; s++) fq_add(acc, acc, x.read_part(s)[n]);
+        x.publish(2 + j, x.lane(i), acc);
+    }
+    x.sync();
+}
 template <class X> RK_HD_NOINLINE void lp_mul(X& x, LaneFp12<X>& r, const LaneFp12<X>& a, const LaneFp12<X>& b) {
-    for (int i = 0; i < X::LANES; i++) { x.publish(0, x.lane(i), a.c[i]); x.publish(1, x.lane(i), b.c[i]); }
+    for (int i = 0; i < X::LANES; i++) if (x.sub(i) == 0) { x.publish(0, x.lane(i), a.c[i]); x.publish(1, x.lane(i), b.c[i]); }
     x.sync();
-    for (int i = 0; i < X::LANES; i++) { Fp lo, hi; fp12_mul_lane(x.lane(i), x.read(0), x.read(1), lo, hi); x.publish(2, x.lane(i), lo); x.publish(3, x.lane(i), hi); }
-    x.sync();
+    Fp lo[X::LANES], hi[X::LANES];
+    for (int i = 0; i < X::LANES; i++) fp12_mul_lane(x.lane(i), x.read(0), x.read(1), lo[i], hi[i], x.sub(i), X::SUB);
+    lp_collect(x, lo, hi);
     for (int i = 0; i < X::LANES; i++) fp12_fold_lane(x.lane(i), x.read(2), r.c[i]);
     x.sync();
 }
 template <class X> RK_HD_NOINLINE void lp_sqr(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
-    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
+    for (int i = 0; i < X::LANES; i++) if (x.sub(i) == 0) x.publish(0, x.lane(i), a.c[i]);
     x.sync();
-    for (int i = 0; i < X::LANES; i++) { Fp lo, hi; fp12_sqr_lane(x.lane(i), x.read(0), lo, hi); x.publish(2, x.lane(i), lo); x.publish(3, x.lane(i), hi); }
-    x.sync();
+    Fp lo[X::LANES], hi[X::LANES];
+    for (int i = 0; i < X::LANES; i++) fp12_sqr_lane(x.lane(i), x.read(0), lo[i], hi[i], x.sub(i), X::SUB);
+    lp_collect(x, lo, hi);
     for (int i = 0; i < X::LANES; i++) fp12_fold_lane(x.lane(i), x.read(2), r.c[i]);
     x.sync();
 }
 template <class X> RK_HD_NOINLINE void lp_line(X& x, LaneFp12<X>& r, const LaneFp12<X>& a, const LineCoeffs& l) {
-    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
+    for (int i = 0; i < X::LANES; i++) if (x.sub(i) == 0) x.publish(0, x.lane(i), a.c[i]);
     x.sync();
-    for (int i = 0; i < X::LANES; i++) { Fp lo, hi; fp12_line_lane(x.lane(i), x.read(0), l, lo, hi); x.publish(2, x.lane(i), lo); x.publish(3, x.lane(i), hi); }
-    x.sync();
+    Fp lo[X::LANES], hi[X::LANES];
+    for (int i = 0; i < X::LANES; i++) fp12_line_lane(x.lane(i), x.read(0), l, lo[i], hi[i], x.sub(i), X::SUB);
+    lp_collect(x, lo, hi);
     for (int i = 0; i < X::LANES; i++) fp12_fold_lane(x.lane(i), x.read(2), r.c[i]);
     x.sync();
 }
 template <class TAB, class X> RK_HD_NOINLINE void lp_frob(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
-    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
+    for (int i = 0; i < X::LANES; i++) if (x.sub(i) == 0) x.publish(0, x.lane(i), a.c[i]);
     x.sync();
-    for (int i = 0; i < X::LANES; i++) fp12_frob_lane<TAB>(x.lane(i), x.read(0), r.c[i]);
+    if (X::SUB == 1) {
+        for (int i = 0; i < X::LANES; i++) fp12_frob_lane<TAB>(x.lane(i), x.read(0), r.c[i]);
+        x.sync();
+        return;
+    }
+    for (int i = 0; i < X::LANES; i++) {               // the two products on sub-lanes 0 and 1, every sub-lane adds them
+        if (x.sub(i) > 1) continue;
+        Fp part;
+        fp12_frob_lane<TAB>(x.lane(i), x.read(0), part, x.sub(i), 2);
+        x.publish_part(x.sub(i), x.lane(i), part);
+    }
+    x.sync();
+    for (int i = 0; i < X::LANES; i++) fq_add(r.c[i], x.read_part(0)[x.lane(i)], x.read_part(1)[x.lane(i)]);
     x.sync();
 }
 template <class X> RK_HD void lp_conj(X& x, LaneFp12<X>& r, const LaneFp12<X>& a) {
@@ -578,7 +622,7 @@ template <class X> RK_HD_NOINLINE bool lp_inv(X& x, LaneFp12<X>& r, const LaneFp
     lp_frob<FP12_FROB2>(x, f4, f2);
     lp_mul(x, m, f2, f4);
     lp_mul(x, n2, n6, m);                                   // = x + y w^6, every other coefficient 0
-    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), n2.c[i]);
+    for (int i = 0; i < X::LANES; i++) if (x.sub(i) == 0) x.publish(0, x.lane(i), n2.c[i]);
     x.sync();
     const Fp* n = x.read(0);
     Fp xx = n[0], yy = n[6], t, u, den, dinv;
@@ -603,7 +647,7 @@ template <class X> RK_HD_NOINLINE bool lp_inv(X& x, LaneFp12<X>& r, const LaneFp
     return true;
 }
 template <class X> RK_HD bool lp_is_one(X& x, const LaneFp12<X>& a) {
-    for (int i = 0; i < X::LANES; i++) x.publish(0, x.lane(i), a.c[i]);
+    for (int i = 0; i < X::LANES; i++) if (x.sub(i) == 0) x.publish(0, x.lane(i), a.c[i]);
     x.sync();
     const Fp* c = x.read(0);
     Fp one;
@@ -659,14 +703,21 @@ RK_HD bool lane_pairing_product_is_one(X& x, const G1Affine* ps, const int* p_in
     return lp_is_one(x, d);
 }
 
-// host / single-thread exchange: one thread plays all 12 lanes
-struct HostLanes {
-    static constexpr int LANES = 12;
+// host / single-thread exchange: one thread plays all 12 lanes (x S sub-lanes)
+template <int S>
+struct HostLanesT {
+    static constexpr int SUB = S;
+    static constexpr int LANES = 12 * S;
     Fp slot[4][12];                                // slots 2 and 3 are read as one 24-entry array (t[0..23])
-    RK_HD int lane(int i) const { return i; }
+    Fp part[S][24];
+    RK_HD int lane(int i) const { return i % 12; }
+    RK_HD int sub(int i) const { return i / 12; }
     RK_HD void publish(int s, int k, const Fp& v) { slot[s][k] = v; }
+    RK_HD void publish_part(int s, int n, const Fp& v) { part[s][n] = v; }
     RK_HD void sync() {}
     RK_HD const Fp* read(int s) const { return slot[s]; }
+    RK_HD const Fp* read_part(int s) const { return part[s]; }
 };
+using HostLanes = HostLanesT<1>;
 
 }  // namespace rk

@@ -160,36 +160,50 @@ static void rand_fp12(Fp12& a, uint32_t seed) {
     }
 }
 static bool fp12_same(const Fp12& a, const Fp12& b) { for (int k = 0; k < 12; k++) if (!fq_eq(a.c[k], b.c[k])) return false; return true; }
-static void to_lanes(LaneFp12<HostLanes>& l, const Fp12& a) { for (int k = 0; k < 12; k++) l.c[k] = a.c[k]; }
-static void from_lanes(Fp12& a, const LaneFp12<HostLanes>& l) { for (int k = 0; k < 12; k++) a.c[k] = l.c[k]; }
+}  // extern "C" (templates below)
+template <class X> static void to_lanes(LaneFp12<X>& l, const Fp12& a) { for (int i = 0; i < X::LANES; i++) l.c[i] = a.c[i % 12]; }
+// every sub-lane of a lane must hold the same coefficient; returns false when they differ
+template <class X> static bool from_lanes(Fp12& a, const LaneFp12<X>& l) {
+    for (int k = 0; k < 12; k++) a.c[k] = l.c[k];
+    for (int i = 12; i < X::LANES; i++) if (!fq_eq(l.c[i], l.c[i % 12])) return false;
+    return true;
+}
 // returns 0 when every lane-parallel Fp12 operation equals the scalar one on `iters` random inputs,
-// else a code naming the first operation that differs
-int fc_lane_fp12_ops(int iters) {
-    HostLanes x;
+// else a code naming the first operation that differs (+100 when sub-lanes of one lane disagree)
+template <int S> static int lane_fp12_ops(int iters) {
+    using X = HostLanesT<S>;
+    static X x;
     for (int it = 0; it < iters; it++) {
         Fp12 a, b, want, got;
         rand_fp12(a, 2 * it + 1); rand_fp12(b, 2 * it + 2);
-        LaneFp12<HostLanes> la, lb, lr;
+        static LaneFp12<X> la, lb, lr;
         to_lanes(la, a); to_lanes(lb, b);
-        fp12_mul(want, a, b); lp_mul(x, lr, la, lb); from_lanes(got, lr); if (!fp12_same(want, got)) return 1;
-        fp12_sqr(want, a); lp_sqr(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 2;
+#define RK_SAME(code) do { if (!from_lanes(got, lr)) return 100 + code; if (!fp12_same(want, got)) return code; } while (0)
+        fp12_mul(want, a, b); lp_mul(x, lr, la, lb); RK_SAME(1);
+        fp12_sqr(want, a); lp_sqr(x, lr, la); RK_SAME(2);
         LineCoeffs l; l.l0 = b.c[0]; l.l2 = b.c[1]; l.l3 = b.c[2]; l.l6 = b.c[3]; l.l8 = b.c[4];
-        fp12_mul_line(want, a, l); lp_line(x, lr, la, l); from_lanes(got, lr); if (!fp12_same(want, got)) return 3;
-        fp12_frob<FP12_FROB1>(want, a); lp_frob<FP12_FROB1>(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 4;
-        fp12_frob<FP12_FROB2>(want, a); lp_frob<FP12_FROB2>(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 5;
-        fp12_conj(want, a); lp_conj(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 6;
+        fp12_mul_line(want, a, l); lp_line(x, lr, la, l); RK_SAME(3);
+        fp12_frob<FP12_FROB1>(want, a); lp_frob<FP12_FROB1>(x, lr, la); RK_SAME(4);
+        fp12_frob<FP12_FROB2>(want, a); lp_frob<FP12_FROB2>(x, lr, la); RK_SAME(5);
+        fp12_conj(want, a); lp_conj(x, lr, la); RK_SAME(6);
         if (!fp12_inv(want, a)) return 7;
         if (!lp_inv(x, lr, la)) return 8;
-        from_lanes(got, lr); if (!fp12_same(want, got)) return 9;
-        if (it < 2) { fp12_pow_x(want, a); lp_pow_x(x, lr, la); from_lanes(got, lr); if (!fp12_same(want, got)) return 10; }
+        RK_SAME(9);
+        if (it < 2) { fp12_pow_x(want, a); lp_pow_x(x, lr, la); RK_SAME(10); }
+#undef RK_SAME
     }
     Fp12 z; for (int k = 0; k < 12; k++) fe_zero(z.c[k]);
-    LaneFp12<HostLanes> lz, lr; to_lanes(lz, z);
+    static LaneFp12<X> lz, lr; to_lanes(lz, z);
     if (lp_inv(x, lr, lz)) return 11;                    // 0 has no inverse
     return 0;
 }
+extern "C" {
+// sub = sub-lanes per lane: 1 (one thread per coefficient), 5 and 12 (what the CTA-wide device kernel runs)
+int fc_lane_fp12_ops(int iters, int sub) {
+    return sub == 1 ? lane_fp12_ops<1>(iters) : sub == 5 ? lane_fp12_ops<5>(iters) : sub == 12 ? lane_fp12_ops<12>(iters) : -1;
+}
 // the same check as fc_pairing_check2 through the lane-parallel path with precomputed lines
-int fc_pairing_check2_lanes(const uint8_t* p1, const uint8_t* q1, const uint8_t* p2, const uint8_t* q2) {
+int fc_pairing_check2_lanes(const uint8_t* p1, const uint8_t* q1, const uint8_t* p2, const uint8_t* q2, int sub) {
     G1Affine ps[2]; int inf[2]; G2Affine qs[2];
     int rc = g1_decompress(ps[0], p1); if (rc < 0) return -1; inf[0] = rc == 1;
     rc = g1_decompress(ps[1], p2); if (rc < 0) return -1; inf[1] = rc == 1;
@@ -198,6 +212,7 @@ int fc_pairing_check2_lanes(const uint8_t* p1, const uint8_t* q1, const uint8_t*
     static LineStep l0[PAIRING_STEPS], l1[PAIRING_STEPS];
     pairing_precompute_lines(l0, qs[0]);
     pairing_precompute_lines(l1, qs[1]);
+    if (sub == 12) { static HostLanesT<12> x12; return lane_pairing_product_is_one(x12, ps, inf, l0, l1) ? 1 : 0; }
     HostLanes x;
     return lane_pairing_product_is_one(x, ps, inf, l0, l1) ? 1 : 0;
 }

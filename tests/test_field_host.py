@@ -244,8 +244,10 @@ def test_lane_parallel_fp12_equals_scalar(L):
     """pairing.cuh's lane-parallel Fp12 arithmetic (what k_pairing_check_lanes runs on 12 lanes of a
     warp) against the scalar implementation, operation by operation: product, square, sparse line
     product, both Frobenius maps, conjugation, the norm-based inversion (vs 12 x 12 elimination),
-    exponentiation by |x|; 0 has no inverse."""
-    assert L.fc_lane_fp12_ops(40) == 0
+    exponentiation by |x|; 0 has no inverse.  With 1, 5 and 12 sub-lanes per lane (the CTA-wide kernel
+    k_pairing_check_cta runs 12: one Fp product per thread); the sub-lanes of a lane must agree."""
+    for sub, iters in ((1, 40), (5, 10), (12, 10)):
+        assert L.fc_lane_fp12_ops(iters, sub) == 0, sub
 
 
 def test_lane_parallel_pairing_check(L, pyoracle, golden):
@@ -267,11 +269,13 @@ def test_lane_parallel_pairing_check(L, pyoracle, golden):
         p1 = o.g1_add(o.g1_add(C, o.g1_neg(o.g1_mul(G, (y + dy) % R))), o.g1_mul(PI, z))
         args = (o.g1_compress(p1), be192(g2a), o.g1_compress(o.g1_neg(PI)), be192(g2b))
         assert L.fc_pairing_check2(*args) == want
-        assert L.fc_pairing_check2_lanes(*args) == want
+        assert L.fc_pairing_check2_lanes(*args, 1) == want
+        assert L.fc_pairing_check2_lanes(*args, 12) == want
     # an infinity argument drops its pair: e(inf, Q) e(P, Q') == 1 only if P is infinity too
     inf = b"\xc0" + bytes(47)
-    assert L.fc_pairing_check2_lanes(inf, be192(s.g2[0]), inf, be192(s.g2[1])) == 1
-    assert L.fc_pairing_check2_lanes(inf, be192(s.g2[0]), o.g1_compress(G), be192(s.g2[1])) == 0
+    for sub in (1, 12):
+        assert L.fc_pairing_check2_lanes(inf, be192(s.g2[0]), inf, be192(s.g2[1]), sub) == 1
+        assert L.fc_pairing_check2_lanes(inf, be192(s.g2[0]), o.g1_compress(G), be192(s.g2[1]), sub) == 0
 
 
 def test_g1_subgroup_check_by_endomorphism(L, pyoracle):
