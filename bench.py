@@ -412,9 +412,10 @@ def run_ours(args):
         ncpu = max(args.cpu_sample, cores)
         sample = [blobs[i].cpu().numpy().tobytes() for i in range(ncpu)]
         dt, res = cpu_commit_prove(sample, cores)
-        for i in (0, ncpu - 1):
+        for i in range(ncpu):                       # every blob the CPU leg computed is also a parity check of the GPU outputs
             got = tuple(keep[k][i].numpy().tobytes() for k in ("c", "vh", "x", "y", "p"))
-            assert got == res[i]
+            assert got == res[i], "bench output differs from the oracle at blob %d" % i
+        parity_n += ncpu
         dt1, _ = cpu_commit_prove(sample[:4], 1)
         cpu = {"value": ncpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d blobs of the timed batch, one blob per thread on %d threads (oracle/kzg_ref.c)" % (ncpu, cores),
