@@ -404,6 +404,9 @@ constexpr int PAIRING_STEPS = 68;                  // 63 doublings + 5 additions
 
 struct LineStep { Fp l0, l6, a, b; };              // line = l0 + l6 w^6 + (a xP) w^2 + (b xP) w^8 + yP w^3
 
+// The three functions below return LAZY sums: plain limb additions of products (each < 1.2p, cross
+// terms of a square doubled), at most 12 of them, so <= 27p -- lp_collect reduces once, after the
+// partial sums of all sub-lanes have been added.
 // Sub-lanes.  The products of one lane are independent, so a lane may be played by S threads
 // ("sub-lanes"): sub-lane s takes the products whose running number is congruent to s modulo S and
 // the partial sums are added up afterwards (lp_collect).  S = 1: the whole lane, as before.
@@ -415,8 +418,8 @@ RK_HD_NOINLINE void fp12_mul_lane(int k, const Fp* a, const Fp* b, Fp& lo, Fp& h
 #pragma unroll 1
     for (int i = s; i < 12; i += S) {
         Fp m;
-        if (i <= k) { fp_mul_sel<true>(m, a[i], b[k - i]); fq_add(lo, lo, m); }
-        else { fp_mul_sel<true>(m, a[i], b[k + 12 - i]); fq_add(hi, hi, m); }
+        if (i <= k) { fp_mul_sel<true>(m, a[i], b[k - i]); fe_add(lo, lo, m); }
+        else { fp_mul_sel<true>(m, a[i], b[k + 12 - i]); fe_add(hi, hi, m); }
     }
 }
 // lane k: the same for a * a, cross terms once and doubled (7 products)
@@ -433,8 +436,8 @@ RK_HD_NOINLINE void fp12_sqr_lane(int k, const Fp* a, Fp& lo, Fp& hi, int s = 0,
             const int j = n - i;
             Fp m;
             if (i == j) fp_sqr_sel<true>(m, a[i]);
-            else { fp_mul_sel<true>(m, a[i], a[j]); fq_dbl(m, m); }
-            fq_add(t, t, m);
+            else { fp_mul_sel<true>(m, a[i], a[j]); fe_add(m, m, m); }
+            fe_add(t, t, m);
         }
     }
 }
@@ -447,22 +450,33 @@ RK_HD_NOINLINE void fp12_line_lane(int k, const Fp* a, const LineCoeffs& l, Fp& 
         const int e = es[q];
         const Fp& c = e == 0 ? l.l0 : e == 2 ? l.l2 : e == 3 ? l.l3 : e == 6 ? l.l6 : l.l8;
         Fp m;
-        if (e <= k) { fp_mul_sel<true>(m, a[k - e], c); fq_add(lo, lo, m); }
-        else { fp_mul_sel<true>(m, a[k + 12 - e], c); fq_add(hi, hi, m); }
+        if (e <= k) { fp_mul_sel<true>(m, a[k - e], c); fe_add(lo, lo, m); }
+        else { fp_mul_sel<true>(m, a[k + 12 - e], c); fe_add(hi, hi, m); }
     }
 }
 // lane k: coefficient k after folding t[0..22] (t[23] ignored) modulo w^12 = 2 w^6 - 2.
 //   w^(12+j) = 2 w^(6+j) - 2 w^j            (j <= 5)
 //   w^(12+j) = 2 w^j - 4 w^(j-6)            (6 <= j <= 10)
 RK_HD_NOINLINE void fp12_fold_lane(int k, const Fp* t, Fp& out) {
-    Fp r = t[k], d;
+    // Lazy: plain limb additions / subtractions against a multiple of p that covers the subtrahend
+    // (inputs <= 2p), ONE loose reduction and a conditional subtraction at the end -- half the limb
+    // passes of doing every step in the strict (<= 2p) domain.
+    Fp r, d;
     if (k <= 5) {
-        fq_dbl(d, t[12 + k]); fq_sub(r, r, d);                         // - 2 T_k
-        if (k <= 4) { fq_dbl(d, t[18 + k]); fq_dbl(d, d); fq_sub(r, r, d); }   // - 4 T_(k+6)
+        fe_add(d, t[12 + k], t[12 + k]);                               // 2 T_k <= 4p
+        fe_sub<FpTag, 4>(r, t[k], d);                                  // t_k - 2 T_k + 4p <= 6p
+        if (k <= 4) {
+            fe_add(d, t[18 + k], t[18 + k]); fe_add(d, d, d);          // 4 T_(k+6) <= 8p
+            fe_sub<FpTag, 8>(r, r, d);                                 // <= 14p
+        }
     } else {
-        fq_dbl(d, t[6 + k]); fq_add(r, r, d);                          // + 2 T_(k-6)
-        if (k <= 10) { fq_dbl(d, t[12 + k]); fq_add(r, r, d); }        // + 2 T_k
+        if (k <= 10) fe_add(d, t[6 + k], t[12 + k]);                   // T_(k-6) + T_k <= 4p
+        else d = t[6 + k];
+        fe_add(d, d, d);                                               // <= 8p
+        fe_add(r, t[k], d);                                            // <= 10p
     }
+    fe_reduce_loose<FpTag>(r);
+    fe_cond_sub_k<2>(r);
     out = r;
 }
 // lane k: coefficient k of a^(p^e) (TAB = FP12_FROB1 / FP12_FROB2): two products
@@ -537,7 +551,12 @@ struct LaneFp12 {
 // raw coefficients (lo, hi) of every played thread -> t[0..23] in slots 2 | 3
 template <class X> RK_HD void lp_collect(X& x, const Fp* lo, const Fp* hi) {
     if (X::SUB == 1) {
-        for (int i = 0; i < X::LANES; i++) { x.publish(2, x.lane(i), lo[i]); x.publish(3, x.lane(i), hi[i]); }
+        for (int i = 0; i < X::LANES; i++) {
+            Fp l = lo[i], h = hi[i];                    // lazy sums (<= 27p) -> strict
+            fe_reduce_loose<FpTag>(l); fe_cond_sub_k<2>(l);
+            fe_reduce_loose<FpTag>(h); fe_cond_sub_k<2>(h);
+            x.publish(2, x.lane(i), l); x.publish(3, x.lane(i), h);
+        }
         x.sync();
         return;
     }
@@ -547,8 +566,12 @@ template <class X> RK_HD void lp_collect(X& x, const Fp* lo, const Fp* hi) {
         const int j = x.sub(i);                         // sub-lane 0 adds up t[k], sub-lane 1 t[12 + k]
         if (j > 1) continue;
         const int n = 12 * j + x.lane(i);
+        // the sub-lanes' lazy partial sums, <= 27p in total: plain limb additions (one carry pass each, no
+        // comparison against the modulus), then ONE loose reduction and a conditional subtraction: below 2p
         Fp acc = x.read_part(0)[n];
-        for (int s = 1; s < X::SUB; s++) fq_add(acc, acc, x.read_part(s)[n]);
+        for (int s = 1; s < X::SUB; s++) fe_add(acc, acc, x.read_part(s)[n]);
+        fe_reduce_loose<FpTag>(acc);
+        fe_cond_sub_k<2>(acc);
         x.publish(2 + j, x.lane(i), acc);
     }
     x.sync();
