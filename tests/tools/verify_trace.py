@@ -30,4 +30,4 @@ for _ in range(5):
 bad = bytearray(praw); bad[48 * 7:48 * 8] = praw[48 * 8:48 * 9]
 assert verify(bytes(bad)) == 0
 print("n=%d pairing_lanes=%s verify wall ms: %s  best %.2f ms = %.0f blobs/s; accept ok, reject-after-swap ok" %
-      (n, os.environ.get("RAIKO_KZG_PAIRING_LANES", "1"), ["%.1f" % (1e3 * t) for t in ts], 1e3 * min(ts), n / min(ts)), flush=True)
+      (n, os.environ.get("RAIKO_KZG_PAIRING_LANES", "2 (default: CTA-wide)"), ["%.1f" % (1e3 * t) for t in ts], 1e3 * min(ts), n / min(ts)), flush=True)
