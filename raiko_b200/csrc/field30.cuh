@@ -126,6 +126,8 @@ using Fr = Fe<FrTag>;
 //   2  row-interleaved: product row i is followed at once by reduction row i and the window of
 //      N+1 live columns slides down one limb, so the product needs 28 accumulator registers
 //      instead of 52; one split pass (at bit 32) in the middle keeps every column below 2^64.
+//   4  = 3 + 1: the library default.  5 = 3 with the square done the same way (77 instead of 91
+//      multiply-accumulates; measured slower).
 //   3  form 0 with one level of subtractive Karatsuba on the product rows (fe_mul only):
 //      a = A0 + A1 X, X = 2^(30 H), H = ceil(N / 2):  a b = A0 B0 + X (A0 B0 + A1 B1 + (A0 - A1)(B1 - B0))
 //      + X^2 A1 B1 -- 134 multiply-accumulates instead of 169 for N = 13, the differences are signed
@@ -133,7 +135,7 @@ using Fr = Fe<FrTag>;
 //      two's-complement columns), the columns end up holding exactly what form 0 computes.
 // ---------------------------------------------------------------------------
 #ifndef RK_MUL_FORM
-#define RK_MUL_FORM 3
+#define RK_MUL_FORM 4
 #endif
 
 // lo + 4 * up as one multiply-add (IMAD.WIDE with an immediate multiplicand is full rate; stated as a
@@ -172,7 +174,7 @@ RK_HD void mont_reduce_columns(Fe<F>& r, uint64_t (&c)[2 * F::N]) {
     // columns first (carry-save: no ripple, every step independent).
     constexpr int HOT_LO = 7, HOT_HI = 2 * N - 2 - 7;
     if (HOT_LO <= HOT_HI) {
-#if RK_MUL_FORM == 1
+#if RK_MUL_FORM == 1 || RK_MUL_FORM == 4
         split_columns32<HOT_LO, HOT_HI, 2 * N>(c);
 #else
         uint64_t carry_in = 0;
@@ -236,7 +238,7 @@ RK_HD int32_t launder_s(int32_t x) {
 template <class F>
 RK_HD void fe_mul(Fe<F>& r, const Fe<F>& a, const Fe<F>& b) {
     constexpr int N = F::N;
-#if RK_MUL_FORM == 3
+#if RK_MUL_FORM == 3 || RK_MUL_FORM == 4 || RK_MUL_FORM == 5   // 4 = 3 with the hot-column split of form 1, 5 = 3 with a Karatsuba square too
     constexpr int H = (N + 1) / 2, L = N - H;         // low half H limbs, high half L <= H limbs
     uint64_t c[2 * N];
 #pragma unroll
@@ -306,7 +308,48 @@ RK_HD void fe_sqr(Fe<F>& r, const Fe<F>& a) {
     uint32_t a2[N];
 #pragma unroll
     for (int i = 0; i < N; i++) a2[i] = launder(a.v[i] << 1);
-#if RK_MUL_FORM == 2
+#if RK_MUL_FORM == 5
+    // a^2 = A0^2 + X (A0^2 + A1^2 - (A0 - A1)^2) + X^2 A1^2: 77 multiply-accumulates instead of 91 for N = 13
+    constexpr int H = (N + 1) / 2, L = N - H;
+    uint64_t c[2 * N];
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) c[k] = 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+        mac(c[2 * i], a.v[i], a.v[i]);
+#pragma unroll
+        for (int j = i + 1; j < H; j++) mac(c[i + j], a2[i], a.v[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        mac(c[2 * H + 2 * i], a.v[H + i], a.v[H + i]);
+#pragma unroll
+        for (int j = i + 1; j < L; j++) mac(c[2 * H + i + j], a2[H + i], a.v[H + j]);
+    }
+    {
+        uint64_t u[2 * H - 1];
+#pragma unroll
+        for (int j = 0; j < 2 * H - 1; j++) u[j] = c[j] + (j < 2 * L - 1 ? c[2 * H + j] : 0);
+#pragma unroll
+        for (int j = 0; j < 2 * H - 1; j++) c[H + j] += u[j];
+    }
+    {
+        int32_t d[H], nd[H], nd2[H];
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+            d[i] = launder_s((int32_t)a.v[i] - (i < L ? (int32_t)a.v[H + i] : 0));     // |d| < 2^30
+            nd[i] = launder_s(-d[i]);
+            nd2[i] = launder_s(-2 * d[i]);                                               // |2d| < 2^31
+        }
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+            mac_signed(c[H + 2 * i], nd[i], d[i]);
+#pragma unroll
+            for (int j = i + 1; j < H; j++) mac_signed(c[H + i + j], nd2[i], d[j]);
+        }
+    }
+    mont_reduce_columns<F>(r, c);
+#elif RK_MUL_FORM == 2
     // Row i adds a_i^2 (weight 2i) and the doubled products 2 a_i a_j, j > i: a column gathers its
     // product weight earlier than in the general product (up to 2 units of 2^60 per row from
     // products plus one from the reduction), so the window is split after rows 3 and 7.

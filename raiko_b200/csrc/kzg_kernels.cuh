@@ -241,7 +241,7 @@ constexpr int MSM_AFF_MAX_K = 64;
 #define RK_AFF_REGS 128
 #endif
 #ifndef RK_AFF_SYNC
-#define RK_AFF_SYNC 2
+#define RK_AFF_SYNC 4                  // lockstep groups of 4 warps (2 before the Karatsuba product rows; re-measured after)
 #endif
 // 1: fused limb passes in the backward loop (raw x1 + x2, conditional negation folded into the
 // subtraction, subtraction + loose reduction in one pass against a shared-memory table of multiples

@@ -37,7 +37,7 @@ def val(a, bits=30):
     return sum(int(x) << (bits * i) for i, x in enumerate(a))
 
 
-@pytest.mark.parametrize("form", [None, 0, 1, 2, 3])
+@pytest.mark.parametrize("form", [None, 0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("name,mod,n", [("fp", P, 13), ("fr", R, 9)])
 def test_montgomery_mul_sqr(form, name, mod, n):
     """Every formulation of the Montgomery product (field30.cuh RK_MUL_FORM), worst-case column
