@@ -33,6 +33,39 @@ def test_verify_every_golden_tuple(gpu_settings, golden):
                                        bytes.fromhex(p["proof"]), gpu_settings), (case["name"], p["label"])
 
 
+def test_pairing_check_kernels_agree_and_are_deterministic(golden):
+    """The three pairing-check kernels (single thread, one warp of 12 lanes, CTA of 12 x 12 sub-lanes:
+    RAIKO_KZG_PAIRING_LANES = 0 / 1 / 2) give the same answers on every golden tuple and on tampered
+    ones, and the CTA-wide one -- whose Fp12 values travel through shared memory between barriers --
+    gives the same answer 25 times in a row (a missing barrier would show up as a flaky verdict)."""
+    import os
+    import raiko_b200 as rk
+    tuples = []
+    for case in golden["cases"]:
+        for p in case["proofs"]:
+            c, z, y, pr = (bytes.fromhex(v) for v in (case["commitment"], p["z"], p["y"], p["proof"]))
+            tuples.append((c, z, y, pr, True))
+            y1 = ((int.from_bytes(y, "big") + 1) % R).to_bytes(32, "big")
+            tuples.append((c, z, y1, pr, False))
+    saved = os.environ.get("RAIKO_KZG_PAIRING_LANES")
+    try:
+        for lanes in ("0", "1", "2"):
+            os.environ["RAIKO_KZG_PAIRING_LANES"] = lanes
+            s = rk.KzgSettings(window_bits=8)
+            sel = tuples if lanes != "0" else tuples[:6]          # the single-thread check takes ~0.1 s per tuple
+            for c, z, y, pr, want in sel:
+                assert rk.verify_kzg_proof(c, z, y, pr, s) == want, (lanes, want)
+            if lanes == "2":
+                for c, z, y, pr, want in tuples[:2]:
+                    assert [rk.verify_kzg_proof(c, z, y, pr, s) for _ in range(25)] == [want] * 25
+            s.close()
+    finally:
+        if saved is None:
+            os.environ.pop("RAIKO_KZG_PAIRING_LANES", None)
+        else:
+            os.environ["RAIKO_KZG_PAIRING_LANES"] = saved
+
+
 def test_verify_rejects_bad_encodings(gpu_settings, golden):
     import raiko_b200 as rk
     case = golden["cases"][4]
