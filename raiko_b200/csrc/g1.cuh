@@ -209,14 +209,14 @@ RK_HD_NOINLINE void g1_scalar_mul(G1Xyzz& r, const G1Affine& p, const uint32_t* 
 // what matters more on a GPU, lanes of a warp with different scalars no longer diverge on every bit
 // (a warp executes a bit's addition if ANY lane has it set: 255 additions per warp in practice).
 // Exceptional cases are g1_add's (complete).  k < 2^256.
-RK_HD_NOINLINE void g1_scalar_mul_w4(G1Xyzz& r, const G1Affine& p, const uint32_t* k) {
+RK_HD_NOINLINE void g1_scalar_mul_w4(G1Xyzz& r, const G1Affine& p, const uint32_t* k, int nibbles = 64) {
     G1Xyzz tab[15];                                   // tab[d - 1] = d * P (XYZZ)
     g1_from_affine(tab[0], p);
     g1_dbl<true>(tab[1], tab[0]);
     for (int d = 2; d < 15; d++) { tab[d] = tab[d - 1]; g1_madd<true>(tab[d], p.x, p.y); }
     G1Xyzz acc;
     g1_set_inf(acc);
-    for (int nib = 63; nib >= 0; nib--) {
+    for (int nib = nibbles - 1; nib >= 0; nib--) {
         for (int s = 0; s < 4; s++) { G1Xyzz t; g1_dbl<true>(t, acc); acc = t; }
         const uint32_t d = (k[nib >> 3] >> (4 * (nib & 7))) & 15u;
         if (d) g1_add<true>(acc, tab[d - 1]);

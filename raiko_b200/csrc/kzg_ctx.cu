@@ -878,7 +878,7 @@ constexpr size_t VERIFY_MAX_N = 16384;
 struct VerifyState {
     int n = 0;
     const uint8_t *d_c = nullptr, *d_p = nullptr;
-    G1Affine *d_pts = nullptr, *d_pair = nullptr;
+    G1Affine *d_pts = nullptr, *d_pts_hi = nullptr, *d_pair = nullptr;   // d_pts_hi: 2^128 * (C_i | proof_i | G)
     int *d_inf = nullptr, *d_pinf = nullptr, *d_flags = nullptr;
     G1Xyzz *d_a = nullptr, *d_e = nullptr, *d_part = nullptr;
     Fr* d_r = nullptr;
@@ -892,7 +892,8 @@ constexpr int VR_PARTS = 64;               // CTAs of the first reduction level
 rk_status verify_begin(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, VerifyState& v, int n, const uint8_t* d_c, const uint8_t* d_p) {
     v.n = n; v.d_c = d_c; v.d_p = d_p;
     CUDA_TRY(buf.alloc(&v.d_pts, 2 * (size_t)n)); CUDA_TRY(buf.alloc(&v.d_inf, 2 * (size_t)n));
-    CUDA_TRY(buf.alloc(&v.d_a, (size_t)n)); CUDA_TRY(buf.alloc(&v.d_e, 3 * (size_t)n)); CUDA_TRY(buf.alloc(&v.d_part, 2 * (size_t)VR_PARTS));
+    CUDA_TRY(buf.alloc(&v.d_pts_hi, 2 * (size_t)n + 1));
+    CUDA_TRY(buf.alloc(&v.d_a, 2 * (size_t)n)); CUDA_TRY(buf.alloc(&v.d_e, 6 * (size_t)n)); CUDA_TRY(buf.alloc(&v.d_part, 2 * (size_t)VR_PARTS));
     CUDA_TRY(buf.alloc(&v.d_r, 1)); CUDA_TRY(buf.alloc(&v.d_pair, 2)); CUDA_TRY(buf.alloc(&v.d_pinf, 2));
     CUDA_TRY(buf.alloc(&v.d_flags, 4)); CUDA_TRY(buf.alloc(&v.d_g2, 384));
     CUDA_TRY(cudaEventCreateWithFlags(&v.ev_inputs, cudaEventDisableTiming));
@@ -906,8 +907,10 @@ rk_status verify_begin(rk_kzg_ctx* ctx, DeviceCtx* d, DevBuf& buf, VerifyState& 
     CUDA_TRY(cudaStreamWaitEvent(side, v.ev_inputs, 0));
     launch_k_g1_decompress_validate((n + 31) / 32, 32, 0, side, d_c, n, v.d_pts, v.d_inf, v.d_flags + 0);
     launch_k_g1_decompress_validate((n + 31) / 32, 32, 0, side, d_p, n, v.d_pts + n, v.d_inf + n, v.d_flags + 1);
+    // 2^128 * every point (and * G): the base points of the scalars' upper halves, independent of the challenge
+    launch_k_verify_pow128((2 * n + 1 + 63) / 64, 64, 0, side, v.d_pts, v.d_inf, 2 * n, v.d_pts_hi);
     CUDA_TRY(cudaEventRecord(v.ev_points, side));
-    d->stats.total_launches += 2;
+    d->stats.total_launches += 3;
     return RK_OK;
 }
 
@@ -926,9 +929,10 @@ rk_status verify_finish(rk_kzg_ctx* ctx, DeviceCtx* d, VerifyState& v, const uin
     mark(1);
     CUDA_TRY(cudaStreamWaitEvent(st, v.ev_points, 0));
     mark(2);
-    launch_k_verify_terms(dim3((unsigned)((n + 63) / 64), 4), 64, 0, st, v.d_r, d_z, d_y, v.d_pts, v.d_inf, v.d_pts + n, v.d_inf + n, n, v.d_a, v.d_e, v.d_flags + 2);
+    launch_k_verify_terms(dim3((unsigned)((n + 63) / 64), 4, 2), 64, 0, st, v.d_r, d_z, d_y, v.d_pts, v.d_inf, v.d_pts + n, v.d_inf + n, n,
+                          v.d_pts_hi, v.d_pts_hi + n, v.d_pts_hi + 2 * n, v.d_a, v.d_e, v.d_flags + 2);
     mark(3);
-    launch_k_verify_reduce_partial(VR_PARTS, VR_THREADS, 0, st, v.d_a, n, v.d_e, 3 * n, v.d_part, v.d_part + VR_PARTS);
+    launch_k_verify_reduce_partial(VR_PARTS, VR_THREADS, 0, st, v.d_a, 2 * n, v.d_e, 6 * n, v.d_part, v.d_part + VR_PARTS);
     launch_k_verify_reduce(1, VR_THREADS, 0, st, v.d_part, v.d_part + VR_PARTS, VR_PARTS, v.d_pair, v.d_pinf);
     mark(4);
     if (d->pairing_lanes >= 2 && d->g2_lines) launch_k_pairing_check_cta(1, PAIRING_CTA_THREADS, 0, st, v.d_pair, v.d_pinf, d->g2_lines, v.d_flags + 3);

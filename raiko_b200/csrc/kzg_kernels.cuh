@@ -1492,14 +1492,32 @@ __global__ void __launch_bounds__(64) k_batch_challenge(const uint8_t* c, const 
 //   j = 2:  E_i2 = r^i * C_i                         -> out_e[3 i + 1]
 //   j = 3:  E_i3 = -(r^i y_i) * G                    -> out_e[3 i + 2]
 // so that  sum A = sum r^i proof_i  and  sum E = sum r^i (C_i - y_i G + z_i proof_i).
+// hi[i] = 2^128 * pts[i] (affine; infinity flags are those of pts), and hi[n] = 2^128 * G: the upper halves'
+// base points of k_verify_terms.  Independent of the batch challenge r, so it runs beside the transcript hash.
+__global__ void __launch_bounds__(64) k_verify_pow128(const G1Affine* pts, const int* inf, int n, G1Affine* hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    G1Affine p;
+    if (i < n) { if (inf[i]) return; p = pts[i]; }
+    else { fe_const<FpTag, FP_GEN_X>(p.x); fe_const<FpTag, FP_GEN_Y>(p.y); }
+    G1Xyzz acc, t;
+    g1_from_affine(acc, p);
+    for (int s = 0; s < 128; s++) { g1_dbl<true>(t, acc); acc = t; }
+    Fp zinv;
+    fe_inv(zinv, acc.zzz);                                   // a point of prime order r never doubles to infinity
+    g1_to_affine_with_inv(hi[i], acc, zinv);
+}
+
 __global__ void __launch_bounds__(64) k_verify_terms(const Fr* r_mont, const uint8_t* z, const uint8_t* y, const G1Affine* cs,
-                                                      const int* c_inf, const G1Affine* ps, const int* p_inf, int n, G1Xyzz* out_a,
-                                                      G1Xyzz* out_e, int* err) {
-    // grid = (ceil(n / 64), 4): blockIdx.y = j selects the term, so every warp walks ONE kind of scalar
+                                                      const int* c_inf, const G1Affine* ps, const int* p_inf, int n,
+                                                      const G1Affine* cs_hi, const G1Affine* ps_hi, const G1Affine* g_hi,
+                                                      G1Xyzz* out_a, G1Xyzz* out_e, int* err) {
+    // grid = (ceil(n / 64), 4, 2): blockIdx.y = j selects the term, so every warp walks ONE kind of scalar
     // multiplication (with j in the lane index the three branches below ran one after the other in
-    // every warp: 16.3 ms per 4096 blobs against 16.3 / 3 and less with the windowed ladder).
+    // every warp: 16.3 ms per 4096 blobs); blockIdx.z = h selects the 128-bit half of the scalar,
+    // k P = k_lo P + k_hi (2^128 P), so a thread walks 128 doublings instead of 256.
     //   j = 0: r^i proof_i    1: (r^i z_i) proof_i    2: r^i C_i    3: -(r^i y_i) G
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, h = blockIdx.z;
     if (i >= n) return;
     Fr base = *r_mont, ri, kc;
     fe_const<FrTag, FR_ONE>(ri);
@@ -1519,14 +1537,16 @@ __global__ void __launch_bounds__(64) k_verify_terms(const Fr* r_mont, const uin
     fe_pack<FrTag>(k, kc);
     G1Affine base_pt;
     bool inf;
-    if (j <= 1) { base_pt = ps[i]; inf = p_inf[i] != 0; }
-    else if (j == 2) { base_pt = cs[i]; inf = c_inf[i] != 0; }
+    if (j <= 1) { base_pt = (h ? ps_hi : ps)[i]; inf = p_inf[i] != 0; }
+    else if (j == 2) { base_pt = (h ? cs_hi : cs)[i]; inf = c_inf[i] != 0; }
+    else if (h) { base_pt = *g_hi; inf = false; }
     else { fe_const<FpTag, FP_GEN_X>(base_pt.x); fe_const<FpTag, FP_GEN_Y>(base_pt.y); inf = false; }
     G1Xyzz t;
     g1_set_inf(t);
-    if (!inf) g1_scalar_mul_w4(t, base_pt, k);
+    if (!inf) g1_scalar_mul_w4(t, base_pt, k + 4 * h, 32);
     if (j == 3 && !g1_is_inf(t)) fe_neg<FpTag, 6>(t.y, t.y);
-    if (j == 0) out_a[i] = t; else out_e[3 * (size_t)i + (j - 1)] = t;
+    const size_t o = (size_t)h * n + i;
+    if (j == 0) out_a[o] = t; else out_e[3 * o + (j - 1)] = t;
 }
 
 // Sums of the terms, two levels.  Level 1: CTA b folds a strided slice of `src` (count points) into

@@ -44,8 +44,9 @@ constexpr size_t PAIRING_LINES_BYTES = 2 * 68 * 4 * sizeof(Fp);   // 2 fixed G2 
     X(k_sha_fs_challenge, (const uint8_t* blobs, const uint8_t* commitments, int nblobs, uint8_t* out_z), (blobs, commitments, nblobs, out_z)) \
     X(k_g1_decompress_validate, (const uint8_t* in, int n, G1Affine* out, int* out_inf, int* err), (in, n, out, out_inf, err)) \
     X(k_batch_challenge, (const uint8_t* c, const uint8_t* z, const uint8_t* y, const uint8_t* pr, int n, Fr* out_r), (c, z, y, pr, n, out_r)) \
-    X(k_verify_terms, (const Fr* r_mont, const uint8_t* z, const uint8_t* y, const G1Affine* cs, const int* c_inf, const G1Affine* ps, const int* p_inf, int n, G1Xyzz* out_a, G1Xyzz* out_e, int* err), \
-      (r_mont, z, y, cs, c_inf, ps, p_inf, n, out_a, out_e, err))                              \
+    X(k_verify_pow128, (const G1Affine* pts, const int* inf, int n, G1Affine* hi), (pts, inf, n, hi)) \
+    X(k_verify_terms, (const Fr* r_mont, const uint8_t* z, const uint8_t* y, const G1Affine* cs, const int* c_inf, const G1Affine* ps, const int* p_inf, int n, const G1Affine* cs_hi, const G1Affine* ps_hi, const G1Affine* g_hi, G1Xyzz* out_a, G1Xyzz* out_e, int* err), \
+      (r_mont, z, y, cs, c_inf, ps, p_inf, n, cs_hi, ps_hi, g_hi, out_a, out_e, err))           \
     X(k_verify_reduce_partial, (const G1Xyzz* a, int na, const G1Xyzz* e, int ne, G1Xyzz* part_a, G1Xyzz* part_e), (a, na, e, ne, part_a, part_e)) \
     X(k_verify_reduce, (const G1Xyzz* part_a, const G1Xyzz* part_e, int nparts, G1Affine* out_pts, int* out_inf), (part_a, part_e, nparts, out_pts, out_inf))
 
