@@ -860,7 +860,10 @@ __device__ __forceinline__ void cta_sum_fr(Fr& v, Fr* ws, int tid) {
     }
 }
 
-__global__ void __launch_bounds__(FR_THREADS, 2) k_fr_eval_quot(FrParams prm) {
+#ifndef RK_FR_MIN_BLOCKS
+#define RK_FR_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(FR_THREADS, RK_FR_MIN_BLOCKS) k_fr_eval_quot(FrParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // per-element prefix products / inverses live in global scratch (coalesced: thread t touches
     // element k*256 + t), not in shared memory: 147 KB per blob would pin one CTA per SM and leave
